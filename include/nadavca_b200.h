@@ -1,0 +1,144 @@
+/*
+ * nadavca_b200.h -- C ABI of libnadavca_b200.so: the B200 (sm_100a) replacement for nadavca's native DP core.
+ *
+ * The reference exposes its hot path through ONE foreign-function boundary, the pybind11 module `nadavca.dtw`
+ * (/root/reference/nadavca/dtw/dtwmodule.cpp:10-29), called from nadavca/estimator.py:77,99,172.  Every entry
+ * point below names the reference interface it replaces.  The boundary is batched: one call handles a whole
+ * batch of reads (CSR layout: a value array plus an int64 offsets array of n_reads+1 entries per field), because
+ * one read exposes far too little parallelism for a GPU.  A batch of one read is exactly the reference call.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in signatures; `stream` is a cudaStream_t passed as void* (NULL = default
+ *     stream); device pointers are named d_*; everything else is host memory owned by the caller.
+ *   - every int-returning function returns 0 on success, a negative NVB_E* code on failure; nvb_last_error()
+ *     gives the message (thread-local).  There is NO CPU fallback: without a usable CUDA device every compute
+ *     entry point fails with NVB_ECUDA.
+ *   - the library keeps nothing of the caller's buffers after a call returns.
+ */
+#ifndef NADAVCA_B200_H
+#define NADAVCA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NVB_OK 0
+#define NVB_EINVAL (-1)   /* bad argument */
+#define NVB_ECUDA (-2)    /* CUDA runtime error / no device */
+#define NVB_ENOMEM (-3)   /* workspace does not fit the device */
+#define NVB_ESTATE (-4)   /* call order (e.g. download before run) */
+
+/* per-read status written by the refine / estimate calls */
+#define NVB_READ_OK 0
+#define NVB_READ_NO_PATH 1  /* reference: RefineAlignment returns an empty vector (dtw.cpp:211-213) */
+#define NVB_READ_BAD_BAND 2 /* anchors give an empty band row (the reference would throw std::length_error) */
+
+typedef struct nvb_model nvb_model;
+typedef struct nvb_batch nvb_batch;
+
+int nvb_abi_version(void);
+const char *nvb_last_error(void);
+/* number of usable CUDA devices (0 when there is no driver/GPU); never fails */
+int nvb_device_count(void);
+
+/* ---- k-mer model: replaces class KmerModel (dtwmodule.cpp:12-18, kmer_model.cpp:6-42) -------------------- */
+/* mean/sigma have alphabet_size^k entries; tables (mean, log(1/sqrt(2 pi s^2)), 1/(2 s^2)) are built on the host
+ * with the same libm expressions as kmer_model.cpp:10-13 and uploaded to `device`. */
+nvb_model *nvb_model_create(int k, int central_position, int alphabet_size, const double *mean,
+                            const double *sigma, int64_t n_kmers, int device);
+void nvb_model_destroy(nvb_model *model);
+int nvb_model_k(const nvb_model *model);                 /* KmerModel::GetK */
+int nvb_model_central_position(const nvb_model *model);  /* KmerModel::GetCentralPosition */
+int nvb_model_alphabet_size(const nvb_model *model);
+/* KmerModel::GetExpectedSignal (kmer_model.cpp:32-42), batched; runs as a CUDA kernel.
+ * reference/context arrays as in nvb_reads; out has reference_off[n_reads] doubles (host). */
+int nvb_model_expected_signal(nvb_model *model, int32_t n_reads, const int32_t *reference,
+                              const int64_t *reference_off, const int32_t *context_before,
+                              const int64_t *context_before_off, const int32_t *context_after,
+                              const int64_t *context_after_off, double *out);
+
+/* ---- a batch of reads: the arguments shared by refine_alignment / estimate_log_likelihoods ------------- */
+/* (dtwmodule.cpp:19-28: signal, reference, context_before, context_after, approximate_alignment, bandwidth,
+ *  min_event_length).  All pointers are HOST memory. */
+typedef struct nvb_reads {
+  int32_t n_reads;
+  const double *signal;           /* concatenated signal slices */
+  const int64_t *signal_off;      /* [n_reads+1] */
+  const int32_t *reference;       /* concatenated numeric bases (0..alphabet-1) */
+  const int64_t *reference_off;   /* [n_reads+1] */
+  const int32_t *context_before;  /* may be NULL when context_before_off is all zero */
+  const int64_t *context_before_off;
+  const int32_t *context_after;
+  const int64_t *context_after_off;
+  const int32_t *anchors;         /* approximate_alignment: pairs (signal index, reference index) */
+  const int64_t *anchor_off;      /* [n_reads+1], counted in pairs */
+  int32_t bandwidth;
+  int32_t min_event_length;
+} nvb_reads;
+
+/* One-shot calls with HOST buffers (upload -> kernels -> download).  These are the drop-in for the two pybind
+ * functions; host<->device copies happen inside. */
+
+/* refine_alignment (dtwmodule.cpp:24-28 -> RefineAlignment dtw.cpp:133-228).
+ * events: int32[reference_off[n_reads]][2] = (event start, event end) sample offsets into each read's slice;
+ * status: int32[n_reads] (NVB_READ_*); rows of reads without a path are filled with -1. */
+int nvb_refine_alignment_batch(nvb_model *model, const nvb_reads *reads, int model_transitions, int32_t *events,
+                               int32_t *status);
+/* estimate_log_likelihoods (dtwmodule.cpp:19-23 -> EstimateLogLikelihoods dtw.cpp:37-131).
+ * out: double[reference_off[n_reads]][alphabet_size] raw log-likelihoods; status: int32[n_reads]. */
+int nvb_estimate_log_likelihoods_batch(nvb_model *model, const nvb_reads *reads, int model_wobbling, double *out,
+                                       int32_t *status);
+
+/* ---- resident batches: inputs uploaded once, results kept in HBM ----------------------------------------- */
+/* Upload a batch and compute its band geometry (ComputeBandStarts/Ends dtw.cpp:7-35) on the device. */
+nvb_batch *nvb_batch_create(nvb_model *model, const nvb_reads *reads);
+void nvb_batch_destroy(nvb_batch *batch);
+/* replace the signal values (same offsets), e.g. after Read.tweak_signal_normalization (estimator.py:96-97) */
+int nvb_batch_set_signal(nvb_batch *batch, const double *signal);
+/* limit for the DP matrices kept in HBM at one time (bytes; 0 = 70% of the free device memory).  Batches that
+ * need more are processed in several waves of reads. */
+int nvb_batch_set_workspace_limit(nvb_batch *batch, int64_t bytes);
+/* run the kernels on `stream`; asynchronous with respect to the host except for wave planning */
+int nvb_batch_refine(nvb_batch *batch, int model_transitions, void *stream);
+int nvb_batch_estimate(nvb_batch *batch, int model_wobbling, void *stream);
+/* results of the last run (blocking copies) */
+int nvb_batch_get_events(nvb_batch *batch, int32_t *events, int32_t *status);
+int nvb_batch_get_log_likelihoods(nvb_batch *batch, double *out, int32_t *status);
+/* band geometry, for tests and cell counting: starts/ends int32[reference_off[n]+n_reads] (n_r+1 rows per read) */
+int nvb_batch_get_bands(nvb_batch *batch, int32_t *starts, int32_t *ends);
+/* DP cell counts of the batch by the formulas of SURVEY.md 8(d): [0] refine with transitions, [1] refine without,
+ * [2] estimate forward+backward, [3] estimate SNP loop */
+int nvb_batch_cell_counts(nvb_batch *batch, int model_wobbling, int64_t counts[4]);
+/* device pointers of resident results (valid until the next run / destroy): raw log-likelihoods
+ * double[sum n][alphabet], events int32[sum n][2], status int32[n_reads] */
+double *nvb_batch_d_log_likelihoods(nvb_batch *batch);
+int32_t *nvb_batch_d_events(nvb_batch *batch);
+int32_t *nvb_batch_d_status(nvb_batch *batch);
+/* number of kernels launched by this batch object so far (bench.py reports it as gpu_launches) */
+int64_t nvb_batch_launch_count(const nvb_batch *batch);
+
+/* ---- estimator post-processing on the device (nadavca/estimator.py) ------------------------------------------ */
+/* (n,3) alignment table of get_refined_alignment (estimator.py:187-195):
+ * out int64[sum n][3] = (reference position, event_start + start_in_signal, event_end + start_in_signal);
+ * reference position = ref_start + i (forward) or ref_end - i - 1 (reverse strand). Host buffers. */
+int nvb_batch_get_alignment_table(nvb_batch *batch, const int64_t *start_in_signal, const int64_t *ref_start,
+                                  const int64_t *ref_end, const int32_t *reverse, int64_t *out);
+/* _normalize_log_likelihoods + reverse-strand complement/flip (estimator.py:45-47,111-119) applied to the
+ * resident raw log-likelihoods; d_chunks: double[sum n][4] device buffer (alphabet must be 4). */
+int nvb_batch_chunk_values(nvb_batch *batch, const int32_t *reverse, double normalization_event_length,
+                           double *d_chunks, void *stream);
+/* consensus accumulation (estimator.py:226-231): d_acc[dest[r] + i][j] += chunk_r[i][j], d_cov[dest[r]+i] += 1
+ * for every read r with dest[r] >= 0 and status OK.  dest is a HOST array of n_reads row offsets. */
+int nvb_batch_scatter_add(nvb_batch *batch, const double *d_chunks, const int64_t *dest, double *d_acc,
+                          int32_t *d_cov, void *stream);
+/* _compute_posterior (estimator.py:123-156) over concatenated groups: d_ll double[total][4], d_ref int8[total]
+ * (0..3, anything else = no base matches), group_off HOST int64[n_groups+1]; d_out double[total][4]. */
+int nvb_posterior(int device, const double *d_ll, const int8_t *d_ref, const int64_t *group_off,
+                  int32_t n_groups, int k, double snp_prior, double *d_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NADAVCA_B200_H */

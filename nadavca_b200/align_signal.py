@@ -1,0 +1,84 @@
+"""align_signal() -- reference nadavca/align_signal.py:13-81, batched on the GPU."""
+import sys
+
+import numpy as np
+from scipy.stats import linregress
+
+from . import defaults
+from .alignment import ApproximateAligner
+from .estimator import ProbabilityEstimator
+from .genome import Genome
+from .kmer_model import KmerModel
+from .read import Read
+
+
+def load_model_and_estimator(reference_filename, config=defaults.CONFIG_FILE, kmer_model=None,
+                             bwa_executable=defaults.BWA_EXECUTABLE, aligner=None, reference=None):
+    """align_signal.py:13-41 -> (kmer_model, ProbabilityEstimator) or None when a file is missing."""
+    if kmer_model is None:
+        kmer_model = defaults.KMER_MODEL_FILE
+    try:
+        config = defaults.load_config(config)
+    except FileNotFoundError:
+        sys.stderr.write('failed to load config: {} not found\n'.format(config))
+        return None
+    if isinstance(kmer_model, str):
+        kmer_model = KmerModel.load_from_hdf5(kmer_model)
+    if aligner is None:
+        try:
+            references = Genome.load_from_fasta(reference_filename)
+        except FileNotFoundError:
+            sys.stderr.write("failed to process: reference {} doesn't exist\n".format(reference_filename))
+            return None
+        references_dict = {r.description[1:]: r.bases for r in references}
+        aligner = ApproximateAligner(bwa_executable, reference, reference_filename, references_dict)
+    return kmer_model, ProbabilityEstimator(kmer_model, aligner, config)
+
+
+def _linear_renormalization(kmer_model, read, apx_alignment, alignment):
+    """One even renorm round (align_signal.py:59-76): regress per-event means on the expected levels and rescale
+    the whole normalised signal."""
+    bases_num = Genome.to_numerical(apx_alignment.reference_part)
+    expected = np.array(kmer_model.get_expected_signal(bases_num, [], []))
+    signal_cut = read.normalized_signal[alignment[0][1]:alignment[-1][2]]
+    al_start = alignment[0][1]
+    signal_means = [np.mean(signal_cut[s - al_start:e - al_start]) for _, s, e in alignment]
+    slope, intercept, _, _, _ = linregress(expected, signal_means)
+    read.normalized_signal = (read.normalized_signal - intercept) / slope
+
+
+def align_signal(reference_filename,
+                 reads,
+                 config=defaults.CONFIG_FILE,
+                 kmer_model=defaults.KMER_MODEL_FILE,
+                 bwa_executable=defaults.BWA_EXECUTABLE,
+                 group_name=defaults.GROUP_NAME,
+                 renorm_rounds=defaults.RENORM_ROUNDS,
+                 aligner=None,
+                 reference=None):
+    """Generator of ``(read, (approximate_alignment, alignment))`` like the reference (align_signal.py:43-81);
+    `alignment` is an int (n,3) array [reference position, event_start, event_end].  Accepts ``Read`` instances
+    (fast5 file names need h5py and are out of scope).  Reads without an alignment yield ``(read, None)`` as the
+    reference's README promises.  All reads go through each stage as one GPU batch: refine -> linear
+    renormalisation (round 0) -> refine (round 1) -> linear renormalisation (round 2)."""
+    loaded = load_model_and_estimator(reference_filename, config, kmer_model, bwa_executable, aligner, reference)
+    if loaded is None:
+        return
+    kmer_model, estimator = loaded
+    reads = list(reads)
+    for i, read in enumerate(reads):
+        if isinstance(read, str):
+            reads[i] = Read.load_from_fast5(read, group_name)
+        Read.normalize_reads([reads[i]])  # per-read median/MAD (align_signal.py:54)
+    results = estimator.get_refined_alignments(reads)
+    for r in range(renorm_rounds):
+        alive = [i for i, res in enumerate(results) if res is not None]
+        if r % 2 == 0:
+            for i in alive:
+                _linear_renormalization(kmer_model, reads[i], *results[i])
+        else:
+            again = estimator.get_refined_alignments([reads[i] for i in alive])
+            for i, res in zip(alive, again):
+                results[i] = res
+    for read, res in zip(reads, results):
+        yield read, res

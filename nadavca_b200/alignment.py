@@ -1,0 +1,106 @@
+"""Approximate (basecall-level) alignment contract (reference nadavca/alignment.py).
+
+``ApproximateSignalAlignment`` and ``signal_alignment_from_base_mapping`` keep the exact layout of
+``ApproximateAligner.get_signal_alignment`` (alignment.py:142-186).  Running BWA is host work outside the scope of
+this package: any object with ``get_signal_alignment(read, bandwidth)`` can be the aligner.
+"""
+from collections import namedtuple
+
+import numpy
+
+from .genome import Genome
+
+ApproximateSignalAlignment = namedtuple('ApproximateSignalAlignment',
+                                        ['alignment',
+                                         'signal_range',
+                                         'reference_range',
+                                         'read_sequence_range',
+                                         'reverse_complement',
+                                         'reference_part',
+                                         'contig_name'])
+
+
+def parse_cigar(cigar):
+    """'12M3D' -> [(12,'M'),(3,'D')] (alignment.py:42-52)."""
+    result, num = [], 0
+    for character in cigar:
+        if character.isdigit():
+            num = num * 10 + int(character)
+        else:
+            result.append((num, character))
+            num = 0
+    return result
+
+
+def base_mapping_from_cigar(cigar, mapped_position, read_sequence, reference, is_reverse_complement):
+    """CIGAR walk keeping only matching bases as anchors, flipped to read orientation for the reverse strand
+    (alignment.py:109-140)."""
+    oriented = Genome.reverse_complement(read_sequence) if is_reverse_complement else numpy.asarray(read_sequence)
+    index_in_read, index_in_reference = 0, mapped_position
+    mapping = []
+    for num, operation in parse_cigar(cigar):
+        if operation == 'S' or operation == 'I':
+            index_in_read += num
+        elif operation == 'D':
+            index_in_reference += num
+        elif operation == 'M':
+            same = numpy.nonzero(numpy.asarray(reference[index_in_reference:index_in_reference + num]) ==
+                                 oriented[index_in_read:index_in_read + num])[0]
+            mapping.extend((index_in_read + int(i), index_in_reference + int(i)) for i in same)
+            index_in_read += num
+            index_in_reference += num
+        else:
+            raise ValueError('Unknown cigar operation: {}'.format(operation))
+    if is_reverse_complement:
+        mapping = [(len(read_sequence) - 1 - r, len(reference) - 1 - g) for r, g in mapping]
+        mapping.reverse()
+    return numpy.array(mapping, dtype=int).reshape(-1, 2)
+
+
+def signal_alignment_from_base_mapping(read, base_mapping, is_reverse_complement, contig_name, reference,
+                                       bandwidth):
+    """alignment.py:142-186: base anchors -> (signal index, reference index) anchors, ranges and reference part.
+
+    `base_mapping` holds (index in read.sequence, index in the reference) pairs in read orientation -- for the
+    reverse strand the reference index counts from the END of the contig, as the reference's CIGAR walk produces."""
+    mapping = read.sequence_to_signal_mapping
+    pairs = [(mapping[int(r)], int(g)) for r, g in base_mapping if int(r) in mapping]  # convert_mapping, :58-63
+    signal_mapping = numpy.array(pairs, dtype=int).reshape(-1, 2)
+    if len(signal_mapping) == 0:
+        return None
+    start_in_reference = signal_mapping[0][1]
+    end_in_reference = signal_mapping[-1][1] + 1
+    signal_mapping[:, 1] -= start_in_reference
+    if is_reverse_complement:
+        start_in_reference, end_in_reference = len(reference) - end_in_reference, len(reference) - start_in_reference
+    start_in_signal = signal_mapping[0][0]
+    end_in_signal = signal_mapping[-1][0] + 1
+    extended_start = max(0, start_in_signal - bandwidth)
+    extended_end = min(len(read.normalized_signal), end_in_signal + bandwidth)
+    signal_mapping[:, 0] -= extended_start
+    reference_part = reference[start_in_reference:end_in_reference]
+    if is_reverse_complement:
+        reference_part = Genome.reverse_complement(reference_part)
+    return ApproximateSignalAlignment(alignment=signal_mapping,
+                                      signal_range=(extended_start, extended_end),
+                                      reference_range=(int(start_in_reference), int(end_in_reference)),
+                                      read_sequence_range=(int(base_mapping[0][0]), int(base_mapping[-1][0]) + 1),
+                                      reverse_complement=bool(is_reverse_complement),
+                                      reference_part=reference_part,
+                                      contig_name=contig_name)
+
+
+class ApproximateAligner:
+    """Placeholder with the reference's constructor (alignment.py:19-40).  Mapping reads with BWA is host work that
+    stays outside this package; plug in any aligner object exposing ``get_signal_alignment(read, bandwidth)``
+    (``signal_alignment_from_base_mapping`` builds its return value from a CIGAR-derived base mapping)."""
+
+    def __init__(self, bwa_executable, reference, reference_filename, references_dict=None):
+        self.bwa_executable = bwa_executable
+        self.reference = reference
+        self.references_dict = references_dict
+        self.reference_filename = reference_filename
+
+    def get_signal_alignment(self, read, bandwidth):
+        raise NotImplementedError('BWA mapping is out of scope for nadavca_b200: pass an `aligner` object that '
+                                  'implements get_signal_alignment(read, bandwidth)')

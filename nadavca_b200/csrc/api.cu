@@ -1,0 +1,574 @@
+// api.cu -- host side of the C ABI declared in include/nadavca_b200.h: model tables, resident batches, wave
+// planning (how many reads' DP matrices fit in HBM at once) and kernel orchestration.  No CPU compute path.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/nadavca_b200.h"
+#include "kernels.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(expr)                                                                                      \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      return fail(NVB_ECUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, __LINE__, #expr); \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    release();
+    cudaError_t e = cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) n = count; else p = nullptr;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+template <class T>
+cudaError_t upload(DevBuf<T> &buf, const T *src, size_t count, cudaStream_t st) {
+  cudaError_t e = buf.alloc(count);
+  if (e != cudaSuccess) return e;
+  if (count == 0) return cudaSuccess;
+  return cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, st);
+}
+
+}  // namespace
+
+struct nvb_model {
+  int device = 0;
+  ModelDev dev{};
+  DevBuf<double> mean, ac, mc;
+};
+
+struct nvb_batch {
+  nvb_model *model = nullptr;
+  int n_reads = 0;
+  int64_t total_ref = 0, total_sig = 0;
+  std::vector<int64_t> sig_off, ref_off, ctxb_off, ctxa_off, anc_off;
+  // device inputs
+  DevBuf<double> d_signal;
+  DevBuf<int64_t> d_sig_off, d_ref_off, d_ctxb_off, d_ctxa_off, d_anc_off;
+  DevBuf<int32_t> d_ref, d_ctxb, d_ctxa, d_anchors;
+  // band geometry
+  DevBuf<int32_t> d_bs, d_be, d_flags, d_maxw;
+  DevBuf<int64_t> d_cell_off, d_summary;
+  std::vector<int64_t> cells, w0, wn;  // per read: sum of widths over n+1 band rows, first / last width
+  std::vector<int32_t> maxw, flags;
+  // results
+  DevBuf<int32_t> d_events, d_status;
+  DevBuf<double> d_ll;
+  bool have_events = false, have_ll = false;
+  // workspace
+  DevBuf<double> d_prefix, d_suffix, d_dp;
+  DevBuf<int64_t> d_mat_base, d_dp_base;
+  int64_t ws_limit = 0;
+  int64_t launches = 0;
+  BatchDev dev{};
+};
+
+extern "C" {
+
+int nvb_abi_version(void) { return 1; }
+
+const char *nvb_last_error(void) { return g_err.c_str(); }
+
+int nvb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+nvb_model *nvb_model_create(int k, int central_position, int alphabet_size, const double *mean,
+                            const double *sigma, int64_t n_kmers, int device) {
+  if (k <= 0 || alphabet_size < 2 || central_position < 0 || central_position >= k || !mean || !sigma) {
+    fail(NVB_EINVAL, "nvb_model_create: bad arguments");
+    return nullptr;
+  }
+  int64_t expect = 1;
+  for (int i = 0; i < k; i++) expect *= alphabet_size;
+  if (n_kmers != expect) {
+    fail(NVB_EINVAL, "nvb_model_create: expected %lld k-mers, got %lld", (long long)expect, (long long)n_kmers);
+    return nullptr;
+  }
+  if (nvb_device_count() <= device || device < 0) {
+    fail(NVB_ECUDA, "nvb_model_create: CUDA device %d not available (no CPU fallback)", device);
+    return nullptr;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) { fail(NVB_ECUDA, "cudaSetDevice(%d) failed", device); return nullptr; }
+  nvb_model *m = new nvb_model();
+  m->device = device;
+  std::vector<double> ac(n_kmers), mc(n_kmers);
+  for (int64_t i = 0; i < n_kmers; i++) {  // same expressions as kmer_model.cpp:10-13, host libm
+    double s = sigma[i];
+    ac[i] = log(1 / sqrt(2 * M_PI * s * s));
+    mc[i] = 1 / (2 * s * s);
+  }
+  if (upload(m->mean, mean, (size_t)n_kmers, 0) != cudaSuccess || upload(m->ac, ac.data(), (size_t)n_kmers, 0) != cudaSuccess ||
+      upload(m->mc, mc.data(), (size_t)n_kmers, 0) != cudaSuccess || cudaStreamSynchronize(0) != cudaSuccess) {
+    fail(NVB_ECUDA, "nvb_model_create: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete m;
+    return nullptr;
+  }
+  m->dev.k = k; m->dev.central = central_position; m->dev.alphabet = alphabet_size; m->dev.n_kmers = n_kmers;
+  m->dev.mean = m->mean.p; m->dev.ac = m->ac.p; m->dev.mc = m->mc.p;
+  m->dev.log_p_in = log(0.01);
+  return m;
+}
+
+void nvb_model_destroy(nvb_model *model) {
+  if (!model) return;
+  cudaSetDevice(model->device);
+  delete model;
+}
+
+int nvb_model_k(const nvb_model *m) { return m ? m->dev.k : 0; }
+int nvb_model_central_position(const nvb_model *m) { return m ? m->dev.central : 0; }
+int nvb_model_alphabet_size(const nvb_model *m) { return m ? m->dev.alphabet : 0; }
+
+}  // extern "C"
+
+namespace {
+
+int check_offsets(const int64_t *off, int n, const char *what) {
+  if (!off) return fail(NVB_EINVAL, "%s offsets are NULL", what);
+  if (off[0] != 0) return fail(NVB_EINVAL, "%s offsets must start at 0", what);
+  for (int i = 0; i < n; i++)
+    if (off[i + 1] < off[i]) return fail(NVB_EINVAL, "%s offsets are not monotone at read %d", what, i);
+  return NVB_OK;
+}
+
+// Upload the sequence part of a batch (reference + contexts); enough for expected_signal.
+int upload_sequences(nvb_batch *b, int n_reads, const int32_t *reference, const int64_t *reference_off,
+                     const int32_t *cb, const int64_t *cb_off, const int32_t *ca, const int64_t *ca_off,
+                     cudaStream_t st) {
+  int rc;
+  if ((rc = check_offsets(reference_off, n_reads, "reference"))) return rc;
+  if ((rc = check_offsets(cb_off, n_reads, "context_before"))) return rc;
+  if ((rc = check_offsets(ca_off, n_reads, "context_after"))) return rc;
+  b->n_reads = n_reads;
+  b->ref_off.assign(reference_off, reference_off + n_reads + 1);
+  b->ctxb_off.assign(cb_off, cb_off + n_reads + 1);
+  b->ctxa_off.assign(ca_off, ca_off + n_reads + 1);
+  b->total_ref = b->ref_off[n_reads];
+  const int A = b->model->dev.alphabet;
+  for (int64_t i = 0; i < b->total_ref; i++)
+    if (reference[i] < 0 || reference[i] >= A) return fail(NVB_EINVAL, "reference base %d out of range at %lld", reference[i], (long long)i);
+  for (int64_t i = 0; i < b->ctxb_off[n_reads]; i++)
+    if (cb[i] < 0 || cb[i] >= A) return fail(NVB_EINVAL, "context_before base out of range");
+  for (int64_t i = 0; i < b->ctxa_off[n_reads]; i++)
+    if (ca[i] < 0 || ca[i] >= A) return fail(NVB_EINVAL, "context_after base out of range");
+  CU(upload(b->d_ref, reference, (size_t)b->total_ref, st));
+  CU(upload(b->d_ref_off, reference_off, (size_t)n_reads + 1, st));
+  CU(upload(b->d_ctxb, cb, (size_t)b->ctxb_off[n_reads], st));
+  CU(upload(b->d_ctxb_off, cb_off, (size_t)n_reads + 1, st));
+  CU(upload(b->d_ctxa, ca, (size_t)b->ctxa_off[n_reads], st));
+  CU(upload(b->d_ctxa_off, ca_off, (size_t)n_reads + 1, st));
+  b->dev.n_reads = n_reads;
+  b->dev.ref = b->d_ref.p; b->dev.ref_off = b->d_ref_off.p;
+  b->dev.ctxb = b->d_ctxb.p; b->dev.ctxb_off = b->d_ctxb_off.p;
+  b->dev.ctxa = b->d_ctxa.p; b->dev.ctxa_off = b->d_ctxa_off.p;
+  return NVB_OK;
+}
+
+int batch_init(nvb_batch *b, const nvb_reads *r) {
+  cudaStream_t st = 0;
+  const int n = r->n_reads;
+  int rc;
+  if (n < 0) return fail(NVB_EINVAL, "n_reads < 0");
+  if (r->bandwidth < 0 || r->min_event_length < 0) return fail(NVB_EINVAL, "bandwidth / min_event_length must be >= 0");
+  if (r->min_event_length > 1022) return fail(NVB_EINVAL, "min_event_length > 1022 is not supported");
+  if ((rc = check_offsets(r->signal_off, n, "signal"))) return rc;
+  if ((rc = check_offsets(r->anchor_off, n, "anchor"))) return rc;
+  if ((rc = upload_sequences(b, n, r->reference, r->reference_off, r->context_before, r->context_before_off,
+                             r->context_after, r->context_after_off, st)))
+    return rc;
+  b->sig_off.assign(r->signal_off, r->signal_off + n + 1);
+  b->anc_off.assign(r->anchor_off, r->anchor_off + n + 1);
+  b->total_sig = b->sig_off[n];
+  for (int i = 0; i < n; i++) {
+    if (b->sig_off[i + 1] - b->sig_off[i] > 0x7fffff00LL) return fail(NVB_EINVAL, "signal of read %d too long", i);
+    if (b->ref_off[i + 1] - b->ref_off[i] > 0x3fffff00LL) return fail(NVB_EINVAL, "reference of read %d too long", i);
+  }
+  CU(upload(b->d_signal, r->signal, (size_t)b->total_sig, st));
+  CU(upload(b->d_sig_off, r->signal_off, (size_t)n + 1, st));
+  CU(upload(b->d_anchors, r->anchors, (size_t)b->anc_off[n] * 2, st));
+  CU(upload(b->d_anc_off, r->anchor_off, (size_t)n + 1, st));
+  CU(b->d_bs.alloc((size_t)b->total_ref + n));
+  CU(b->d_be.alloc((size_t)b->total_ref + n));
+  CU(b->d_cell_off.alloc((size_t)b->total_ref + 2 * (size_t)n));
+  CU(b->d_flags.alloc(n));
+  CU(b->d_maxw.alloc(n));
+  CU(b->d_summary.alloc((size_t)4 * n));
+  CU(b->d_status.alloc(n));
+  BatchDev &d = b->dev;
+  d.signal = b->d_signal.p; d.sig_off = b->d_sig_off.p;
+  d.anchors = b->d_anchors.p; d.anc_off = b->d_anc_off.p;
+  d.bandwidth = r->bandwidth; d.mel = r->min_event_length;
+  d.bs = b->d_bs.p; d.be = b->d_be.p; d.cell_off = b->d_cell_off.p;
+  d.flags = b->d_flags.p; d.max_width = b->d_maxw.p;
+  nvbk_band(d, b->d_summary.p, st);
+  b->launches++;
+  CU(cudaGetLastError());
+  std::vector<int64_t> summary((size_t)4 * n);
+  CU(cudaMemcpyAsync(summary.data(), b->d_summary.p, summary.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  b->cells.resize(n); b->w0.resize(n); b->wn.resize(n); b->maxw.resize(n); b->flags.resize(n);
+  for (int i = 0; i < n; i++) {
+    b->cells[i] = summary[4 * i];
+    b->w0[i] = summary[4 * i + 1];
+    b->wn[i] = summary[4 * i + 2];
+    b->maxw[i] = (int32_t)(summary[4 * i + 3] & 0xffffffffLL);
+    b->flags[i] = (summary[4 * i + 3] >> 32) ? NVB_READ_BAD_BAND : 0;
+  }
+  return NVB_OK;
+}
+
+int64_t matrix_cells(const nvb_batch *b, int i, int mode) {
+  if (b->flags[i]) return 0;
+  if (mode == NVB_MODE_TRANS) return 2 * b->cells[i] - b->w0[i] - b->wn[i];
+  return b->cells[i];
+}
+
+struct Wave { int b0, b1; };
+
+// Split the batch into waves of consecutive reads whose two DP matrices (+ path scratch) fit the workspace limit.
+int plan_waves(nvb_batch *b, int mode, bool need_dp, std::vector<Wave> &waves, std::vector<int64_t> &mat_base,
+               std::vector<int64_t> &dp_base, int64_t &max_cells, int64_t &max_dp) {
+  int64_t limit = b->ws_limit;
+  if (limit <= 0) {
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    // memory already held by this batch's workspace can be reused
+    free_b += (b->d_prefix.n + b->d_suffix.n + b->d_dp.n) * sizeof(double);
+    limit = (int64_t)(free_b * 0.7);
+  }
+  const int n = b->n_reads;
+  mat_base.assign(n, 0); dp_base.assign(n, 0);
+  waves.clear();
+  max_cells = 0; max_dp = 0;
+  int i = 0;
+  while (i < n) {
+    int64_t cells = 0, dp = 0;
+    int j = i;
+    while (j < n) {
+      int64_t c = matrix_cells(b, j, mode), d = need_dp ? 2 * (int64_t)b->maxw[j] : 0;
+      int64_t bytes = ((cells + c) * 2 + (dp + d)) * (int64_t)sizeof(double);
+      if (bytes > limit && j > i) break;
+      if (bytes > limit)
+        return fail(NVB_ENOMEM, "read %d needs %lld bytes of DP workspace, limit is %lld", j, (long long)bytes, (long long)limit);
+      mat_base[j] = cells; dp_base[j] = dp;
+      cells += c; dp += d;
+      j++;
+    }
+    waves.push_back({i, j});
+    max_cells = std::max(max_cells, cells);
+    max_dp = std::max(max_dp, dp);
+    i = j;
+  }
+  return NVB_OK;
+}
+
+int prepare_workspace(nvb_batch *b, int mode, bool need_dp, std::vector<Wave> &waves, cudaStream_t st) {
+  std::vector<int64_t> mat_base, dp_base;
+  int64_t max_cells = 0, max_dp = 0;
+  int rc = plan_waves(b, mode, need_dp, waves, mat_base, dp_base, max_cells, max_dp);
+  if (rc) return rc;
+  if (b->d_prefix.alloc((size_t)max_cells) != cudaSuccess || b->d_suffix.alloc((size_t)max_cells) != cudaSuccess ||
+      b->d_dp.alloc((size_t)max_dp) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(NVB_ENOMEM, "cannot allocate %lld bytes of DP workspace", (long long)((2 * max_cells + max_dp) * 8));
+  }
+  CU(upload(b->d_mat_base, mat_base.data(), mat_base.size(), st));
+  CU(upload(b->d_dp_base, dp_base.data(), dp_base.size(), st));
+  // pageable-host uploads above are complete when cudaMemcpyAsync returns only for small sizes; be explicit:
+  CU(cudaStreamSynchronize(st));
+  return NVB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+nvb_batch *nvb_batch_create(nvb_model *model, const nvb_reads *reads) {
+  if (!model || !reads) { fail(NVB_EINVAL, "nvb_batch_create: NULL argument"); return nullptr; }
+  if (cudaSetDevice(model->device) != cudaSuccess) { fail(NVB_ECUDA, "cudaSetDevice failed"); return nullptr; }
+  nvb_batch *b = new nvb_batch();
+  b->model = model;
+  if (batch_init(b, reads) != NVB_OK) { delete b; return nullptr; }
+  return b;
+}
+
+void nvb_batch_destroy(nvb_batch *batch) {
+  if (!batch) return;
+  cudaSetDevice(batch->model->device);
+  delete batch;
+}
+
+int nvb_batch_set_signal(nvb_batch *b, const double *signal) {
+  if (!b || !signal) return fail(NVB_EINVAL, "nvb_batch_set_signal: NULL argument");
+  CU(cudaSetDevice(b->model->device));
+  CU(cudaMemcpy(b->d_signal.p, signal, (size_t)b->total_sig * sizeof(double), cudaMemcpyHostToDevice));
+  return NVB_OK;
+}
+
+int nvb_batch_set_workspace_limit(nvb_batch *b, int64_t bytes) {
+  if (!b) return fail(NVB_EINVAL, "NULL batch");
+  b->ws_limit = bytes;
+  return NVB_OK;
+}
+
+int nvb_batch_refine(nvb_batch *b, int model_transitions, void *stream) {
+  if (!b) return fail(NVB_EINVAL, "NULL batch");
+  CU(cudaSetDevice(b->model->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int mode = model_transitions ? NVB_MODE_TRANS : NVB_MODE_PLAIN;
+  std::vector<Wave> waves;
+  int rc = prepare_workspace(b, mode, true, waves, st);
+  if (rc) return rc;
+  CU(b->d_events.alloc((size_t)2 * b->total_ref));
+  for (const Wave &w : waves) {
+    nvbk_sweep(b->model->dev, b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->d_prefix.p, b->d_suffix.p, st);
+    nvbk_path(b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->d_prefix.p, b->d_suffix.p, b->d_dp.p, b->d_dp_base.p,
+              b->d_events.p, b->d_status.p, st);
+    b->launches += 2;
+  }
+  CU(cudaGetLastError());
+  b->have_events = true;
+  return NVB_OK;
+}
+
+int nvb_batch_estimate(nvb_batch *b, int model_wobbling, void *stream) {
+  if (!b) return fail(NVB_EINVAL, "NULL batch");
+  CU(cudaSetDevice(b->model->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const ModelDev &M = b->model->dev;
+  const int mode = model_wobbling ? NVB_MODE_WOBBLE : NVB_MODE_PLAIN;
+  if ((model_wobbling ? 2 * M.k + 2 : M.k + 1) > 32)
+    return fail(NVB_EINVAL, "k = %d is too large for the SNP kernel (needs 2k+2 <= 32 lanes)", M.k);
+  std::vector<Wave> waves;
+  int rc = prepare_workspace(b, mode, false, waves, st);
+  if (rc) return rc;
+  CU(b->d_ll.alloc((size_t)b->total_ref * M.alphabet));
+  nvbk_fill_status(b->dev, b->d_status.p, b->d_ll.p, M.alphabet, st);
+  b->launches++;
+  for (const Wave &w : waves) {
+    nvbk_sweep(M, b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->d_prefix.p, b->d_suffix.p, st);
+    nvbk_no_snp(M, b->dev, w.b0, w.b1, b->d_mat_base.p, b->d_prefix.p, b->d_suffix.p, b->d_ll.p, st);
+    if (nvbk_snp(M, b->dev, model_wobbling, w.b0, w.b1, b->ref_off[w.b0], b->ref_off[w.b1], b->d_mat_base.p,
+                 b->d_prefix.p, b->d_suffix.p, b->d_ll.p, st))
+      return fail(NVB_EINVAL, "SNP kernel configuration not supported");
+    b->launches += 3;
+  }
+  CU(cudaGetLastError());
+  b->have_ll = true;
+  return NVB_OK;
+}
+
+int nvb_batch_get_events(nvb_batch *b, int32_t *events, int32_t *status) {
+  if (!b) return fail(NVB_EINVAL, "NULL batch");
+  if (!b->have_events) return fail(NVB_ESTATE, "nvb_batch_get_events before nvb_batch_refine");
+  CU(cudaSetDevice(b->model->device));
+  CU(cudaDeviceSynchronize());
+  if (events) CU(cudaMemcpy(events, b->d_events.p, (size_t)2 * b->total_ref * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (status) CU(cudaMemcpy(status, b->d_status.p, (size_t)b->n_reads * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return NVB_OK;
+}
+
+int nvb_batch_get_log_likelihoods(nvb_batch *b, double *out, int32_t *status) {
+  if (!b) return fail(NVB_EINVAL, "NULL batch");
+  if (!b->have_ll) return fail(NVB_ESTATE, "nvb_batch_get_log_likelihoods before nvb_batch_estimate");
+  CU(cudaSetDevice(b->model->device));
+  CU(cudaDeviceSynchronize());
+  if (out) CU(cudaMemcpy(out, b->d_ll.p, (size_t)b->total_ref * b->model->dev.alphabet * sizeof(double), cudaMemcpyDeviceToHost));
+  if (status) CU(cudaMemcpy(status, b->d_status.p, (size_t)b->n_reads * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return NVB_OK;
+}
+
+int nvb_batch_get_bands(nvb_batch *b, int32_t *starts, int32_t *ends) {
+  if (!b) return fail(NVB_EINVAL, "NULL batch");
+  CU(cudaSetDevice(b->model->device));
+  size_t cnt = (size_t)b->total_ref + b->n_reads;
+  if (starts) CU(cudaMemcpy(starts, b->d_bs.p, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (ends) CU(cudaMemcpy(ends, b->d_be.p, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return NVB_OK;
+}
+
+int nvb_batch_cell_counts(nvb_batch *b, int model_wobbling, int64_t counts[4]) {
+  if (!b || !counts) return fail(NVB_EINVAL, "NULL argument");
+  CU(cudaSetDevice(b->model->device));
+  size_t cnt = (size_t)b->total_ref + b->n_reads;
+  std::vector<int32_t> bs(cnt), be(cnt);
+  CU(cudaMemcpy(bs.data(), b->d_bs.p, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(be.data(), b->d_be.p, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  const int k = b->model->dev.k, cp = b->model->dev.central, A = b->model->dev.alphabet;
+  int64_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  for (int r = 0; r < b->n_reads; r++) {
+    if (b->flags[r]) continue;
+    const int n = (int)(b->ref_off[r + 1] - b->ref_off[r]);
+    const int32_t *s = bs.data() + b->ref_off[r] + r, *e = be.data() + b->ref_off[r] + r;
+    auto W = [&](int j) { return (int64_t)(e[j] - s[j] + 1); };
+    for (int rho = 0; rho < 2 * n; rho++) {
+      int64_t w = (rho % 2 == 0) ? W(rho / 2) : W(rho / 2 + 1);
+      if (rho >= 1) c0 += w;
+      if (rho <= 2 * n - 2) c0 += w;
+    }
+    for (int j = 1; j <= n; j++) c1 += W(j);
+    for (int j = 0; j < n; j++) c1 += W(j);
+    for (int i = 0; i < n; i++) c2 += W(i + 1);
+    for (int i = 1; i <= n; i++) c2 += W(i - 1);
+    if (model_wobbling) for (int i = 1; i < n; i++) c2 += 2 * W(i);
+    const int back = k - cp - 1, fwd = cp;
+    for (int i = 0; i < n; i++) {
+      int first = std::max(0, i - back), last = std::min(n - 1, i + fwd);
+      int64_t c = 0;
+      for (int j = first; j <= last; j++) c += W(j + 1) + ((j > 0 && model_wobbling) ? W(j) : 0);
+      if (last + 1 < n && model_wobbling) c += W(last);
+      c3 += (A - 1) * c;
+    }
+  }
+  counts[0] = c0; counts[1] = c1; counts[2] = c2; counts[3] = c3;
+  return NVB_OK;
+}
+
+double *nvb_batch_d_log_likelihoods(nvb_batch *b) { return b && b->have_ll ? b->d_ll.p : nullptr; }
+int32_t *nvb_batch_d_events(nvb_batch *b) { return b && b->have_events ? b->d_events.p : nullptr; }
+int32_t *nvb_batch_d_status(nvb_batch *b) { return b ? b->d_status.p : nullptr; }
+int64_t nvb_batch_launch_count(const nvb_batch *b) { return b ? b->launches : 0; }
+
+int nvb_refine_alignment_batch(nvb_model *model, const nvb_reads *reads, int model_transitions, int32_t *events,
+                               int32_t *status) {
+  nvb_batch *b = nvb_batch_create(model, reads);
+  if (!b) return NVB_EINVAL;
+  int rc = nvb_batch_refine(b, model_transitions, nullptr);
+  if (!rc) rc = nvb_batch_get_events(b, events, status);
+  nvb_batch_destroy(b);
+  return rc;
+}
+
+int nvb_estimate_log_likelihoods_batch(nvb_model *model, const nvb_reads *reads, int model_wobbling, double *out,
+                                       int32_t *status) {
+  nvb_batch *b = nvb_batch_create(model, reads);
+  if (!b) return NVB_EINVAL;
+  int rc = nvb_batch_estimate(b, model_wobbling, nullptr);
+  if (!rc) rc = nvb_batch_get_log_likelihoods(b, out, status);
+  nvb_batch_destroy(b);
+  return rc;
+}
+
+int nvb_model_expected_signal(nvb_model *model, int32_t n_reads, const int32_t *reference,
+                              const int64_t *reference_off, const int32_t *context_before,
+                              const int64_t *context_before_off, const int32_t *context_after,
+                              const int64_t *context_after_off, double *out) {
+  if (!model || !out) return fail(NVB_EINVAL, "NULL argument");
+  CU(cudaSetDevice(model->device));
+  nvb_batch b;
+  b.model = model;
+  int rc = upload_sequences(&b, n_reads, reference, reference_off, context_before, context_before_off,
+                            context_after, context_after_off, 0);
+  if (rc) return rc;
+  // the kernel only touches the sequence fields; give the signal offsets a valid array
+  b.dev.sig_off = b.d_ref_off.p;
+  DevBuf<double> d_out;
+  CU(d_out.alloc((size_t)b.total_ref));
+  nvbk_expected_signal(model->dev, b.dev, b.total_ref, d_out.p, 0);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out, d_out.p, (size_t)b.total_ref * sizeof(double), cudaMemcpyDeviceToHost));
+  return NVB_OK;
+}
+
+int nvb_batch_get_alignment_table(nvb_batch *b, const int64_t *start_in_signal, const int64_t *ref_start,
+                                  const int64_t *ref_end, const int32_t *reverse, int64_t *out) {
+  if (!b || !start_in_signal || !ref_start || !ref_end || !reverse || !out) return fail(NVB_EINVAL, "NULL argument");
+  if (!b->have_events) return fail(NVB_ESTATE, "alignment table requested before nvb_batch_refine");
+  CU(cudaSetDevice(b->model->device));
+  const size_t n = b->n_reads;
+  DevBuf<int64_t> d_meta, d_out;
+  DevBuf<int32_t> d_rev;
+  std::vector<int64_t> meta(3 * n);
+  std::copy(start_in_signal, start_in_signal + n, meta.begin());
+  std::copy(ref_start, ref_start + n, meta.begin() + n);
+  std::copy(ref_end, ref_end + n, meta.begin() + 2 * n);
+  CU(upload(d_meta, meta.data(), meta.size(), 0));
+  CU(upload(d_rev, reverse, n, 0));
+  CU(d_out.alloc((size_t)3 * b->total_ref));
+  nvbk_alignment_table(b->dev, b->d_events.p, b->d_status.p, d_meta.p, d_meta.p + n, d_meta.p + 2 * n, d_rev.p,
+                       b->total_ref, d_out.p, 0);
+  b->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out, d_out.p, (size_t)3 * b->total_ref * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  return NVB_OK;
+}
+
+int nvb_batch_chunk_values(nvb_batch *b, const int32_t *reverse, double normalization_event_length, double *d_chunks,
+                           void *stream) {
+  if (!b || !reverse || !d_chunks) return fail(NVB_EINVAL, "NULL argument");
+  if (!b->have_ll) return fail(NVB_ESTATE, "chunk values requested before nvb_batch_estimate");
+  if (b->model->dev.alphabet != 4) return fail(NVB_EINVAL, "chunk values need alphabet_size == 4");
+  CU(cudaSetDevice(b->model->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  DevBuf<int32_t> d_rev;
+  CU(upload(d_rev, reverse, (size_t)b->n_reads, st));
+  nvbk_chunk_values(b->dev, b->d_ll.p, d_rev.p, normalization_event_length, b->total_ref, d_chunks, st);
+  b->launches++;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(st));  // d_rev is freed on return
+  return NVB_OK;
+}
+
+int nvb_batch_scatter_add(nvb_batch *b, const double *d_chunks, const int64_t *dest, double *d_acc, int32_t *d_cov,
+                          void *stream) {
+  if (!b || !d_chunks || !dest || !d_acc || !d_cov) return fail(NVB_EINVAL, "NULL argument");
+  CU(cudaSetDevice(b->model->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  DevBuf<int64_t> d_dest;
+  CU(upload(d_dest, dest, (size_t)b->n_reads, st));
+  nvbk_scatter_add(b->dev, d_chunks, d_dest.p, b->d_status.p, b->total_ref, d_acc, d_cov, st);
+  b->launches++;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(st));
+  return NVB_OK;
+}
+
+int nvb_posterior(int device, const double *d_ll, const int8_t *d_ref, const int64_t *group_off, int32_t n_groups,
+                  int k, double snp_prior, double *d_out, void *stream) {
+  if (!d_ll || !d_ref || !group_off || !d_out || n_groups < 0) return fail(NVB_EINVAL, "bad argument");
+  if (nvb_device_count() <= device) return fail(NVB_ECUDA, "CUDA device %d not available (no CPU fallback)", device);
+  CU(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  DevBuf<int64_t> d_goff;
+  CU(upload(d_goff, group_off, (size_t)n_groups + 1, st));
+  nvbk_posterior(d_ll, d_ref, d_goff.p, n_groups, group_off[n_groups], k, snp_prior, d_out, st);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(st));
+  return NVB_OK;
+}
+
+}  // extern "C"

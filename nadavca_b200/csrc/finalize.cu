@@ -1,0 +1,150 @@
+// finalize.cu -- elementwise post-processing of the estimator glue, kept on the device so that a batch makes one
+// round trip: alignment table (estimator.py:187-195), normalised / strand-flipped chunks (estimator.py:45-47,
+// 111-119), consensus scatter-add (estimator.py:226-231) and the Bayesian posterior stencil (estimator.py:123-156).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+__device__ __forceinline__ int find_read(const BatchDev &B, int64_t g) {
+  int lo = 0, hi = B.n_reads;  // last read with ref_off <= g (empty reads are skipped by construction)
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (B.ref_off[mid] <= g) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void alignment_table_kernel(BatchDev B, const int32_t *events, const int32_t *status,
+                                       const int64_t *sig_start, const int64_t *ref_start, const int64_t *ref_end,
+                                       const int32_t *reverse, int64_t total, int64_t *out) {
+  int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const int b = find_read(B, g);
+  const int64_t i = g - B.ref_off[b];
+  if (status[b] != 0) { out[3 * g] = -1; out[3 * g + 1] = -1; out[3 * g + 2] = -1; return; }
+  out[3 * g] = reverse[b] ? ref_end[b] - i - 1 : ref_start[b] + i;
+  out[3 * g + 1] = events[2 * g] + sig_start[b];
+  out[3 * g + 2] = events[2 * g + 1] + sig_start[b];
+}
+
+// (LL - LL[0][ref[0]]) / normalization_event_length; reverse strand: complement the columns, flip the rows.
+__global__ void chunk_values_kernel(BatchDev B, const double *ll, const int32_t *reverse, double nel, int64_t total,
+                                    double *chunks) {
+  int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const int b = find_read(B, g);
+  const int64_t r0 = B.ref_off[b];
+  const int64_t n = B.ref_off[b + 1] - r0;
+  const int64_t i = g - r0;
+  const double shift = ll[r0 * 4 + B.ref[r0]];
+  if (reverse[b]) {
+    const double *src = ll + (r0 + (n - 1 - i)) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; j++) chunks[g * 4 + j] = (src[3 - j] - shift) / nel;
+  } else {
+    const double *src = ll + g * 4;
+#pragma unroll
+    for (int j = 0; j < 4; j++) chunks[g * 4 + j] = (src[j] - shift) / nel;
+  }
+}
+
+__global__ void scatter_add_kernel(BatchDev B, const double *chunks, const int64_t *dest, const int32_t *status,
+                                   int64_t total, double *acc, int32_t *cov) {
+  int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const int b = find_read(B, g);
+  if (dest[b] < 0 || status[b] != 0) return;
+  const int64_t p = dest[b] + (g - B.ref_off[b]);
+#pragma unroll
+  for (int j = 0; j < 4; j++) atomicAdd(acc + p * 4 + j, chunks[g * 4 + j]);
+  atomicAdd(cov + p, 1);
+}
+
+// _compute_posterior: window [max(0,i-k+1), min(i+k,L)) inside the position's group, same accumulation order.
+__global__ void posterior_kernel(const double *ll, const int8_t *ref, const int64_t *group_off, int n_groups,
+                                 int64_t total, int k, double snp_prior, double *out) {
+  int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  int lo = 0, hi = n_groups;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (group_off[mid] <= g) lo = mid; else hi = mid;
+  }
+  const int64_t gs = group_off[lo], ge = group_off[lo + 1];
+  const int64_t i = g - gs, L = ge - gs;
+  const int64_t cs = max((int64_t)0, i - k + 1), ce = min(i + k, L);
+  double mx = nvb_neg_inf();
+  for (int64_t i2 = cs; i2 < ce; i2++)
+    for (int j = 0; j < 4; j++) mx = fmax(mx, ll[(gs + i2) * 4 + j]);
+  // _corrected_priors (estimator.py:123-129)
+  const double c = 3.0;
+  const double p1 = 1 - snp_prior, p2 = snp_prior / c;
+  const double snp_h = 1 / (p1 / p2 + (1 - (double)(ce - cs - 1)) * c);
+  const double nonsnp_h = 1 - snp_h * c;
+  double pr[4];
+  const int rb = ref[g];
+  for (int j = 0; j < 4; j++) {
+    const double prior = (j != rb) ? snp_h : nonsnp_h;
+    double v = exp(ll[g * 4 + j] - mx) * prior;
+    if (j == rb) {
+      for (int64_t i2 = cs; i2 < ce; i2++) {
+        if (i2 == i) continue;
+        const int rb2 = ref[gs + i2];
+        for (int j2 = 0; j2 < 4; j2++) {
+          if (j2 == rb2) continue;
+          v += exp(ll[(gs + i2) * 4 + j2] - mx) * snp_h;
+        }
+      }
+    }
+    pr[j] = v;
+  }
+  double sum = 0.0;  // Python's builtin sum() starts from int 0
+  for (int j = 0; j < 4; j++) sum += pr[j];
+  for (int j = 0; j < 4; j++) out[g * 4 + j] = pr[j] / sum;
+}
+
+__global__ void fill_status_kernel(BatchDev B, int32_t *status, double *ll, int alphabet) {
+  const int b = blockIdx.x;
+  const int f = B.flags[b];
+  if (threadIdx.x == 0) status[b] = f;
+  if (f && ll) {
+    const int64_t r0 = B.ref_off[b] * alphabet, r1 = B.ref_off[b + 1] * alphabet;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int64_t x = r0 + threadIdx.x; x < r1; x += blockDim.x) ll[x] = nan;
+  }
+}
+
+inline unsigned blocks_for(int64_t total) { return (unsigned)((total + 255) / 256); }
+
+}  // namespace
+
+void nvbk_alignment_table(const BatchDev &B, const int32_t *d_events, const int32_t *d_status,
+                          const int64_t *d_sig_start, const int64_t *d_ref_start, const int64_t *d_ref_end,
+                          const int32_t *d_reverse, int64_t total, int64_t *d_out, cudaStream_t st) {
+  if (total > 0)
+    alignment_table_kernel<<<blocks_for(total), 256, 0, st>>>(B, d_events, d_status, d_sig_start, d_ref_start,
+                                                              d_ref_end, d_reverse, total, d_out);
+}
+
+void nvbk_chunk_values(const BatchDev &B, const double *d_ll, const int32_t *d_reverse, double nel, int64_t total,
+                       double *d_chunks, cudaStream_t st) {
+  if (total > 0) chunk_values_kernel<<<blocks_for(total), 256, 0, st>>>(B, d_ll, d_reverse, nel, total, d_chunks);
+}
+
+void nvbk_scatter_add(const BatchDev &B, const double *d_chunks, const int64_t *d_dest, const int32_t *d_status,
+                      int64_t total, double *d_acc, int32_t *d_cov, cudaStream_t st) {
+  if (total > 0)
+    scatter_add_kernel<<<blocks_for(total), 256, 0, st>>>(B, d_chunks, d_dest, d_status, total, d_acc, d_cov);
+}
+
+void nvbk_posterior(const double *d_ll, const int8_t *d_ref, const int64_t *d_group_off, int n_groups,
+                    int64_t total, int k, double snp_prior, double *d_out, cudaStream_t st) {
+  if (total > 0)
+    posterior_kernel<<<blocks_for(total), 256, 0, st>>>(d_ll, d_ref, d_group_off, n_groups, total, k, snp_prior,
+                                                        d_out);
+}
+
+void nvbk_fill_status(const BatchDev &B, int32_t *d_status, double *d_ll, int alphabet, cudaStream_t st) {
+  if (B.n_reads > 0) fill_status_kernel<<<B.n_reads, 128, 0, st>>>(B, d_status, d_ll, alphabet);
+}

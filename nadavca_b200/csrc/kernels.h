@@ -1,0 +1,36 @@
+// kernels.h -- host-side launchers of the sm_100a kernels (one per stage of the hot path).
+#pragma once
+#include "common.cuh"
+
+// band.cu
+void nvbk_band(const BatchDev &B, int64_t *d_summary, cudaStream_t st);
+void nvbk_expected_signal(const ModelDev &M, const BatchDev &B, int64_t total, double *d_out, cudaStream_t st);
+
+// rows.cu: forward + backward banded rows for reads [b0,b1) (one warp per read and direction)
+void nvbk_sweep(const ModelDev &M, const BatchDev &B, int mode, int b0, int b1, const int64_t *d_mat_base,
+                double *d_prefix, double *d_suffix, cudaStream_t st);
+// no-SNP total (dtw.cpp:83-85) written into the reference-base column of out_ll
+void nvbk_no_snp(const ModelDev &M, const BatchDev &B, int b0, int b1, const int64_t *d_mat_base,
+                 const double *d_prefix, const double *d_suffix, double *d_out_ll, cudaStream_t st);
+
+// snp.cu: the SNP re-run loop (dtw.cpp:93-129)
+int nvbk_snp(const ModelDev &M, const BatchDev &B, int wobbling, int b0, int b1, int64_t g0, int64_t g1,
+             const int64_t *d_mat_base, const double *d_prefix, const double *d_suffix, double *d_out_ll,
+             cudaStream_t st);
+
+// path.cu: posterior rows, max-product path, traceback (dtw.cpp:199-227)
+void nvbk_path(const BatchDev &B, int mode, int b0, int b1, const int64_t *d_mat_base, double *d_prefix,
+               const double *d_suffix, double *d_dp, const int64_t *d_dp_base, int32_t *d_events,
+               int32_t *d_status, cudaStream_t st);
+
+// finalize.cu
+void nvbk_alignment_table(const BatchDev &B, const int32_t *d_events, const int32_t *d_status,
+                          const int64_t *d_sig_start, const int64_t *d_ref_start, const int64_t *d_ref_end,
+                          const int32_t *d_reverse, int64_t total, int64_t *d_out, cudaStream_t st);
+void nvbk_chunk_values(const BatchDev &B, const double *d_ll, const int32_t *d_reverse, double nel, int64_t total,
+                       double *d_chunks, cudaStream_t st);
+void nvbk_scatter_add(const BatchDev &B, const double *d_chunks, const int64_t *d_dest, const int32_t *d_status,
+                      int64_t total, double *d_acc, int32_t *d_cov, cudaStream_t st);
+void nvbk_posterior(const double *d_ll, const int8_t *d_ref, const int64_t *d_group_off, int n_groups,
+                    int64_t total, int k, double snp_prior, double *d_out, cudaStream_t st);
+void nvbk_fill_status(const BatchDev &B, int32_t *d_status, double *d_ll, int alphabet, cudaStream_t st);

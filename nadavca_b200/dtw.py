@@ -1,0 +1,254 @@
+"""Drop-in for the reference's native module ``nadavca.dtw`` (nadavca/dtw/dtwmodule.cpp:10-29) on top of the
+B200 kernels: ``KmerModel``, ``refine_alignment`` and ``estimate_log_likelihoods`` keep the reference's keyword
+signatures (a batch of one read); ``Batch`` is the batched, device-resident form the estimator uses.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import NadavcaCudaError, ReadsPack  # noqa: F401  (re-exported)
+
+
+class KmerModel:
+    """KmerModel(k, central_position, alphabet_size, mean, sigma) -- dtwmodule.cpp:12-18.
+
+    The per-k-mer tables live on the GPU (created lazily on first use so that a model can be described on a host
+    without CUDA, e.g. by ``KmerModel.load_from_hdf5``)."""
+
+    def __init__(self, k, central_position, alphabet_size, mean, sigma, device=None):
+        self._k = int(k)
+        self._central_position = int(central_position)
+        self._alphabet_size = int(alphabet_size)
+        self.mean = np.ascontiguousarray(mean, dtype=np.float64)
+        self.sigma = np.ascontiguousarray(sigma, dtype=np.float64)
+        if self.mean.shape != self.sigma.shape or self.mean.size != self._alphabet_size ** self._k:
+            raise ValueError('mean and sigma need alphabet_size**k entries')
+        self._device = device
+        self._handle = None
+
+    def get_k(self):
+        return self._k
+
+    def get_central_position(self):
+        return self._central_position
+
+    def get_alphabet_size(self):
+        return self._alphabet_size
+
+    @property
+    def device(self):
+        if self._device is None:
+            self._device = _current_device()
+        return self._device
+
+    @property
+    def handle(self):
+        if self._handle is None:
+            lib = _cabi.require_device()
+            h = lib.nvb_model_create(self._k, self._central_position, self._alphabet_size,
+                                     _cabi.ptr(self.mean, ctypes.c_double), _cabi.ptr(self.sigma, ctypes.c_double),
+                                     self.mean.size, self.device)
+            if not h:
+                raise NadavcaCudaError('nvb_model_create failed: ' + _cabi.last_error())
+            self._handle = ctypes.c_void_p(h)
+        return self._handle
+
+    def __del__(self):
+        if getattr(self, '_handle', None) is not None:
+            try:
+                _cabi.load().nvb_model_destroy(self._handle)
+            except Exception:
+                pass
+            self._handle = None
+
+    def get_expected_signal(self, reference, context_before, context_after):
+        """KmerModel::GetExpectedSignal (kmer_model.cpp:32-42): list of the k-mer means along `reference`."""
+        return self.get_expected_signal_batch([reference], [context_before], [context_after])[0].tolist()
+
+    def get_expected_signal_batch(self, references, contexts_before, contexts_after):
+        n = len(references)
+        pack = ReadsPack([[]] * n, references, contexts_before, contexts_after, [[]] * n, 0, 0)
+        out = np.zeros(pack.total_reference, dtype=np.float64)
+        lib = _cabi.load()
+        _cabi.check(lib.nvb_model_expected_signal(
+            self.handle, n, pack.struct.reference, pack.struct.reference_off, pack.struct.context_before,
+            pack.struct.context_before_off, pack.struct.context_after, pack.struct.context_after_off,
+            _cabi.ptr(out, ctypes.c_double)), 'nvb_model_expected_signal')
+        return [out[pack.reference_off[i]:pack.reference_off[i + 1]] for i in range(n)]
+
+
+def _current_device():
+    """Device ordinal for this process: LOCAL_RANK under torchrun, else torch's current device when torch is
+    already in use, else 0."""
+    import os
+    import sys
+    if 'LOCAL_RANK' in os.environ:
+        return int(os.environ['LOCAL_RANK'])
+    torch = sys.modules.get('torch')
+    if torch is not None and torch.cuda.is_available():
+        return torch.cuda.current_device()
+    return 0
+
+
+class Batch:
+    """A batch of reads resident in HBM (nvb_batch_* of the C ABI)."""
+
+    def __init__(self, kmer_model, signals, references, contexts_before, contexts_after, alignments, bandwidth,
+                 min_event_length, workspace_limit=0):
+        self.model = kmer_model
+        self.pack = ReadsPack(signals, references, contexts_before, contexts_after, alignments, bandwidth,
+                              min_event_length)
+        self.lib = _cabi.require_device()
+        h = self.lib.nvb_batch_create(kmer_model.handle, ctypes.byref(self.pack.struct))
+        if not h:
+            raise NadavcaCudaError('nvb_batch_create failed: ' + _cabi.last_error())
+        self.handle = ctypes.c_void_p(h)
+        if workspace_limit:
+            _cabi.check(self.lib.nvb_batch_set_workspace_limit(self.handle, int(workspace_limit)),
+                        'nvb_batch_set_workspace_limit')
+
+    def close(self):
+        if getattr(self, 'handle', None) is not None:
+            self.lib.nvb_batch_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- inputs -----------------------------------------------------------------------------------------------
+    @property
+    def n_reads(self):
+        return self.pack.n_reads
+
+    def set_signals(self, signals):
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.float64) for s in signals])
+                                    if len(signals) else np.zeros(0), dtype=np.float64)
+        if flat.size != self.pack.total_signal:
+            raise ValueError('replacement signals must keep the batch layout')
+        _cabi.check(self.lib.nvb_batch_set_signal(self.handle, _cabi.ptr(flat, ctypes.c_double)),
+                    'nvb_batch_set_signal')
+
+    # -- kernels ----------------------------------------------------------------------------------------------
+    def refine(self, model_transitions, stream=None):
+        _cabi.check(self.lib.nvb_batch_refine(self.handle, int(bool(model_transitions)), _stream(stream)),
+                    'nvb_batch_refine')
+
+    def estimate(self, model_wobbling, stream=None):
+        _cabi.check(self.lib.nvb_batch_estimate(self.handle, int(bool(model_wobbling)), _stream(stream)),
+                    'nvb_batch_estimate')
+
+    # -- results ----------------------------------------------------------------------------------------------
+    def events(self):
+        """-> (list of int32 (n,2) arrays or None for reads without a path, status array)."""
+        ev = np.zeros((self.pack.total_reference, 2), dtype=np.int32)
+        status = np.zeros(self.n_reads, dtype=np.int32)
+        _cabi.check(self.lib.nvb_batch_get_events(self.handle, _cabi.ptr(ev, ctypes.c_int32),
+                                                  _cabi.ptr(status, ctypes.c_int32)), 'nvb_batch_get_events')
+        off = self.pack.reference_off
+        return [ev[off[i]:off[i + 1]] if status[i] == 0 else None for i in range(self.n_reads)], status
+
+    def log_likelihoods(self):
+        a = self.model.get_alphabet_size()
+        out = np.zeros((self.pack.total_reference, a), dtype=np.float64)
+        status = np.zeros(self.n_reads, dtype=np.int32)
+        _cabi.check(self.lib.nvb_batch_get_log_likelihoods(self.handle, _cabi.ptr(out, ctypes.c_double),
+                                                           _cabi.ptr(status, ctypes.c_int32)),
+                    'nvb_batch_get_log_likelihoods')
+        off = self.pack.reference_off
+        return [out[off[i]:off[i + 1]] for i in range(self.n_reads)], status
+
+    def bands(self):
+        cnt = self.pack.total_reference + self.n_reads
+        starts = np.zeros(cnt, dtype=np.int32)
+        ends = np.zeros(cnt, dtype=np.int32)
+        _cabi.check(self.lib.nvb_batch_get_bands(self.handle, _cabi.ptr(starts, ctypes.c_int32),
+                                                 _cabi.ptr(ends, ctypes.c_int32)), 'nvb_batch_get_bands')
+        off = self.pack.reference_off
+        return [(starts[off[i] + i:off[i + 1] + i + 1], ends[off[i] + i:off[i + 1] + i + 1])
+                for i in range(self.n_reads)]
+
+    def cell_counts(self, model_wobbling=True):
+        """DP cell counts: dict refine_transitions / refine_plain / estimate_fb / estimate_snp."""
+        c = np.zeros(4, dtype=np.int64)
+        _cabi.check(self.lib.nvb_batch_cell_counts(self.handle, int(bool(model_wobbling)),
+                                                   _cabi.ptr(c, ctypes.c_int64)), 'nvb_batch_cell_counts')
+        return {'refine_transitions': int(c[0]), 'refine_plain': int(c[1]), 'estimate_fb': int(c[2]),
+                'estimate_snp': int(c[3])}
+
+    def alignment_tables(self, start_in_signal, ref_start, ref_end, reverse):
+        """(n,3) int64 tables of get_refined_alignment (estimator.py:187-195), None for reads without a path."""
+        out = np.zeros((self.pack.total_reference, 3), dtype=np.int64)
+        s = _cabi.as_array(start_in_signal, np.int64)
+        a = _cabi.as_array(ref_start, np.int64)
+        b = _cabi.as_array(ref_end, np.int64)
+        r = _cabi.as_array(reverse, np.int32)
+        _cabi.check(self.lib.nvb_batch_get_alignment_table(
+            self.handle, _cabi.ptr(s, ctypes.c_int64), _cabi.ptr(a, ctypes.c_int64), _cabi.ptr(b, ctypes.c_int64),
+            _cabi.ptr(r, ctypes.c_int32), _cabi.ptr(out, ctypes.c_int64)), 'nvb_batch_get_alignment_table')
+        off = self.pack.reference_off
+        return [out[off[i]:off[i + 1]] if (off[i + 1] > off[i] and out[off[i], 1] >= 0) else None
+                for i in range(self.n_reads)]
+
+    def chunk_values(self, reverse, normalization_event_length, d_chunks, stream=None):
+        """Normalised, strand-corrected chunk values into the device buffer `d_chunks` (a data pointer)."""
+        r = _cabi.as_array(reverse, np.int32)
+        _cabi.check(self.lib.nvb_batch_chunk_values(self.handle, _cabi.ptr(r, ctypes.c_int32),
+                                                    float(normalization_event_length), ctypes.c_void_p(d_chunks),
+                                                    _stream(stream)), 'nvb_batch_chunk_values')
+
+    def scatter_add(self, d_chunks, dest, d_acc, d_cov, stream=None):
+        d = _cabi.as_array(dest, np.int64)
+        _cabi.check(self.lib.nvb_batch_scatter_add(self.handle, ctypes.c_void_p(d_chunks),
+                                                   _cabi.ptr(d, ctypes.c_int64), ctypes.c_void_p(d_acc),
+                                                   ctypes.c_void_p(d_cov), _stream(stream)), 'nvb_batch_scatter_add')
+
+    @property
+    def launch_count(self):
+        return int(self.lib.nvb_batch_launch_count(self.handle))
+
+
+def _stream(stream):
+    if stream is None:
+        return ctypes.c_void_p(0)
+    return ctypes.c_void_p(int(getattr(stream, 'cuda_stream', stream)))
+
+
+def posterior(device, d_ll, d_ref, group_off, k, snp_prior, d_out, stream=None):
+    """_compute_posterior on the device over concatenated groups (pointers are device data pointers)."""
+    lib = _cabi.require_device()
+    g = _cabi.as_array(group_off, np.int64)
+    _cabi.check(lib.nvb_posterior(int(device), ctypes.c_void_p(d_ll), ctypes.c_void_p(d_ref),
+                                  _cabi.ptr(g, ctypes.c_int64), len(g) - 1, int(k), float(snp_prior),
+                                  ctypes.c_void_p(d_out), _stream(stream)), 'nvb_posterior')
+
+
+# ---- the two functions of the reference module, one read per call ------------------------------------------
+
+def refine_alignment(signal, reference, context_before, context_after, approximate_alignment, bandwidth,
+                     min_event_length, kmer_model, model_transitions):
+    """dtwmodule.cpp:24-28: -> list of [event_start, event_end] per reference base, [] when there is no path."""
+    with Batch(kmer_model, [signal], [reference], [context_before], [context_after], [approximate_alignment],
+               bandwidth, min_event_length) as batch:
+        batch.refine(model_transitions)
+        events, _ = batch.events()
+    return [] if events[0] is None else events[0].tolist()
+
+
+def estimate_log_likelihoods(signal, reference, context_before, context_after, approximate_alignment, bandwidth,
+                             min_event_length, kmer_model, model_wobbling):
+    """dtwmodule.cpp:19-23: -> n x alphabet_size list of raw log-likelihoods."""
+    with Batch(kmer_model, [signal], [reference], [context_before], [context_after], [approximate_alignment],
+               bandwidth, min_event_length) as batch:
+        batch.estimate(model_wobbling)
+        ll, _ = batch.log_likelihoods()
+    return ll[0].tolist()

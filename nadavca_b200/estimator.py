@@ -1,0 +1,321 @@
+"""Batched estimator glue on top of the B200 kernels (reference nadavca/estimator.py).
+
+Same classes and method names as the reference (``Chunk``, ``ProbabilityEstimator`` with
+``get_refined_alignment``, ``_estimate_log_likelihoods``, ``estimate_probabilities``, ``_compute_posterior``), but
+every method that touches the DP gathers ALL reads first and makes one trip to the GPU per stage:
+
+    host: approximate alignment, slicing, contexts            (estimator.py:60-74, 159-170)
+    GPU : refine_alignment(model_transitions=False) batch     (estimator.py:77-87)
+    host: Read.tweak_signal_normalization (scipy spline)      (estimator.py:89-97)
+    GPU : estimate_log_likelihoods batch -> normalise / strand flip -> [consensus scatter-add -> all-reduce]
+          -> Bayesian posterior                                (estimator.py:99-121, 199-236)
+
+torch is used only for device buffers, the current stream and (consensus mode, several ranks) the NCCL all-reduce.
+"""
+import numpy
+
+from . import dtw
+from .alphabet import alphabet
+from .genome import Genome
+
+_REF_LUT = numpy.full(256, 4, dtype=numpy.int8)
+for _i, _b in enumerate(alphabet):
+    _REF_LUT[ord(_b)] = _i
+
+
+def _ref_codes(reference_slice):
+    """Reference characters -> int8 codes 0..3, 4 for anything else (never equal to a base, like the reference's
+    string comparison in estimator.py:141,150)."""
+    arr = numpy.asarray(reference_slice)
+    if arr.dtype.kind in 'iu':
+        return arr.astype(numpy.int8)
+    if arr.size == 0:
+        return numpy.zeros(0, dtype=numpy.int8)
+    return _REF_LUT[arr.astype('S1').view(numpy.uint8)]
+
+
+class Chunk:
+    """estimator.py:7-31."""
+
+    def __init__(self, start, end, values, coverage=None):
+        self.start = start
+        self.end = end
+        self.values = values
+        self.coverage = coverage
+        if coverage is None:
+            self.coverage = numpy.ones(end - start, dtype=int)
+
+    def __lt__(self, other):
+        if self.start == other.start:
+            return self.end < other.end
+        return self.start < other.start
+
+    @staticmethod
+    def print_head(file):
+        file.write('index\tbase\tcoverage\t{}\n'.format('\t'.join(alphabet)))
+
+    def print(self, file, reference):
+        for i in range(self.start, self.end):
+            values_string = '\t'.join(map('{:18.16f}'.format, self.values[i - self.start]))
+            file.write('{}\t{}\t{}\t{}\n'.format(i, reference[i], self.coverage[i - self.start], values_string))
+
+
+class _Prepared:
+    """Per-read host preparation shared by both paths."""
+    __slots__ = ('read', 'apx', 'reference_part', 'signal_range', 'context_before', 'context_after')
+
+
+def group_intervals(intervals):
+    """Overlap groups of (start, end) intervals sorted by (start, end) -- estimator.py:205-220; a chunk starting
+    exactly at the running end opens a new group ('>=').  Returns [(group_start, group_end, [member indices])]."""
+    order = sorted(range(len(intervals)), key=lambda i: (intervals[i][0], intervals[i][1]))
+    groups = []
+    members, cur_start, cur_end = [], None, None
+    for pos, idx in enumerate(order):
+        start, end = intervals[idx]
+        if cur_start is None:
+            cur_start, cur_end = start, end
+        members.append(idx)
+        cur_end = max(cur_end, end)
+        if pos + 1 >= len(order) or intervals[order[pos + 1]][0] >= cur_end:
+            groups.append((cur_start, cur_end, members))
+            members, cur_start, cur_end = [], None, None
+    return groups
+
+
+class ProbabilityEstimator:
+    def __init__(self, kmer_model, aligner, config):
+        self.kmer_model = kmer_model
+        self.aligner = aligner
+        self.bandwidth = config['bandwidth']
+        self.snp_prior = config['snp_prior_probability']
+        self.min_event_length = config['min_event_length']
+        self.model_wobbling = config['model_wobbling']
+        self.model_transitions = config['model_transitions']
+        self.normalization_event_length = config['normalization_event_length']
+        self.tweak_signal_normalization = config['tweak_signal_normalization']
+        self.workspace_limit = config.get('workspace_limit_bytes', 0) if hasattr(config, 'get') else 0
+        self.last_stats = {}
+
+    # ---- small host helpers with the reference's names ------------------------------------------------------
+    def _normalize_log_likelihoods(self, likelihoods, reference):
+        shift = likelihoods[0][reference[0]]
+        return (likelihoods - shift) / self.normalization_event_length
+
+    def _get_read_context(self, read, read_sequence_range):
+        start, end = read_sequence_range
+        k = self.kmer_model.get_k()
+        central_position = self.kmer_model.get_central_position()
+        lo = start - central_position
+        # Python slicing semantics of the reference (estimator.py:53): a negative lower bound wraps around
+        context_before = read.sequence[lo:start]
+        context_after = read.sequence[end:end + k - central_position - 1]
+        return Genome.to_numerical(context_before), Genome.to_numerical(context_after)
+
+    def _corrected_priors(self, context_positions):
+        c = len(alphabet) - 1
+        p_1 = 1 - self.snp_prior
+        p_2 = self.snp_prior / c
+        snp_hypothesis_prior = 1 / (p_1 / p_2 + (1 - context_positions) * c)
+        nonsnp_hypothesis_prior = 1 - snp_hypothesis_prior * c
+        return snp_hypothesis_prior, nonsnp_hypothesis_prior
+
+    def _prepare(self, read, reference=None):
+        apx = self.aligner.get_signal_alignment(read, self.bandwidth)
+        if apx is None:
+            return None
+        item = _Prepared()
+        item.read = read
+        item.apx = apx
+        if reference is None:  # get_refined_alignment uses the aligner's reference part (estimator.py:164)
+            part = apx.reference_part
+        else:                  # _estimate_log_likelihoods slices the given reference (estimator.py:64-68)
+            start, end = apx.reference_range
+            part = reference[start:end]
+            if apx.reverse_complement:
+                part = Genome.reverse_complement(part)
+        item.reference_part = Genome.to_numerical(part)
+        item.signal_range = apx.signal_range
+        item.context_before, item.context_after = self._get_read_context(read, apx.read_sequence_range)
+        return item
+
+    def _batch(self, items, signals):
+        return dtw.Batch(self.kmer_model, signals, [it.reference_part for it in items],
+                         [it.context_before for it in items], [it.context_after for it in items],
+                         [it.apx.alignment for it in items], self.bandwidth, self.min_event_length,
+                         workspace_limit=self.workspace_limit)
+
+    # ---- path A: refined alignments ---------------------------------------------------------------------------
+    def get_refined_alignments(self, reads):
+        """Batched get_refined_alignment: list (one per read) of (ApproximateSignalAlignment, int (n,3) array) or
+        None for reads that are unaligned or have no valid path."""
+        prepared = [self._prepare(read) for read in reads]
+        items = [it for it in prepared if it is not None]
+        results = [None] * len(reads)
+        if not items:
+            return results
+        signals = [it.read.normalized_signal[it.signal_range[0]:it.signal_range[1]] for it in items]
+        with self._batch(items, signals) as batch:
+            batch.refine(self.model_transitions)
+            tables = batch.alignment_tables([it.signal_range[0] for it in items],
+                                            [it.apx.reference_range[0] for it in items],
+                                            [it.apx.reference_range[1] for it in items],
+                                            [int(it.apx.reverse_complement) for it in items])
+            self.last_stats = {'launches': batch.launch_count}
+        pos = 0
+        for i, it in enumerate(prepared):
+            if it is None:
+                continue
+            table = tables[pos]
+            pos += 1
+            if table is not None:
+                results[i] = (it.apx, table.astype(int))
+        return results
+
+    def get_refined_alignment(self, read):
+        """estimator.py:158-196 (a batch of one)."""
+        return self.get_refined_alignments([read])[0]
+
+    # ---- path B: log-likelihood chunks ---------------------------------------------------------------------------
+    def _run_estimate(self, reference, reads):
+        """Shared front half of path B.  Returns (items, batch) with raw log-likelihoods resident on the device, or
+        ([], None).  Reads whose approximate alignment or refinement fails are dropped (the reference returns None /
+        crashes in splrep for them)."""
+        items = [it for it in (self._prepare(read, reference) for read in reads) if it is not None]
+        if not items:
+            return [], None
+        signals = [it.read.normalized_signal[it.signal_range[0]:it.signal_range[1]] for it in items]
+        batch = self._batch(items, signals)
+        if self.tweak_signal_normalization:
+            batch.refine(False)
+            events, _ = batch.events()
+            expected = self.kmer_model.get_expected_signal_batch([it.reference_part for it in items],
+                                                                 [it.context_before for it in items],
+                                                                 [it.context_after for it in items])
+            keep = [i for i, ev in enumerate(events) if ev is not None]
+            if len(keep) != len(items):
+                batch.close()
+                items = [items[i] for i in keep]
+                events = [events[i] for i in keep]
+                expected = [expected[i] for i in keep]
+                if not items:
+                    return [], None
+                signals = [signals[i] for i in keep]
+                batch = self._batch(items, signals)
+            for it, ev, exp_sig in zip(items, events, expected):
+                it.read.tweak_signal_normalization(ev.astype(int) + it.signal_range[0], exp_sig)
+            batch.set_signals([it.read.tweaked_normalized_signal[it.signal_range[0]:it.signal_range[1]]
+                               for it in items])
+        batch.estimate(self.model_wobbling)
+        return items, batch
+
+    def _estimate_log_likelihoods(self, reference, read):
+        """estimator.py:59-121 for one read: Chunk of normalised, strand-corrected log-likelihoods or None."""
+        chunks = self.estimate_log_likelihood_chunks(reference, [read])
+        return chunks[0] if chunks else None
+
+    def estimate_log_likelihood_chunks(self, reference, reads):
+        import torch
+        items, batch = self._run_estimate(reference, reads)
+        if batch is None:
+            return []
+        try:
+            total = batch.pack.total_reference
+            d_chunks = torch.empty((total, 4), dtype=torch.float64, device=_device(self.kmer_model))
+            batch.chunk_values([int(it.apx.reverse_complement) for it in items], self.normalization_event_length,
+                               d_chunks.data_ptr(), torch.cuda.current_stream())
+            values = d_chunks.cpu().numpy()
+            off = batch.pack.reference_off
+        finally:
+            batch.close()
+        return [Chunk(it.apx.reference_range[0], it.apx.reference_range[1], values[off[i]:off[i + 1]].copy())
+                for i, it in enumerate(items)]
+
+    def _compute_posterior(self, log_likelihoods, reference):
+        """estimator.py:131-156 for one group, on the device."""
+        import torch
+        dev = _device(self.kmer_model)
+        ll = torch.as_tensor(numpy.ascontiguousarray(log_likelihoods, dtype=numpy.float64), device=dev)
+        ref = torch.as_tensor(_ref_codes(reference), device=dev)
+        out = torch.empty_like(ll)
+        dtw.posterior(dev.index, ll.data_ptr(), ref.data_ptr(), [0, ll.shape[0]], self.kmer_model.get_k(),
+                      self.snp_prior, out.data_ptr(), torch.cuda.current_stream())
+        return out.cpu().numpy()
+
+    def estimate_probabilities(self, reference, reads, independent=False, process_group=None):
+        """estimator.py:199-236.  `independent=True` treats every read as its own group (what estimate_snps does
+        with one call per read, estimate_snps.py:63-68) and returns one Chunk per aligned read in input order.
+        Otherwise chunks are summed per overlap group; with an initialised torch.distributed `process_group` the
+        reads given to each rank are that rank's shard and the per-position sums are all-reduced over NCCL."""
+        import torch
+        items, batch = self._run_estimate(reference, reads)
+        dev = _device(self.kmer_model)
+        stream = torch.cuda.current_stream()
+        dist = _dist(process_group)
+        intervals = [tuple(it.apx.reference_range) for it in items]
+        if dist is not None and not independent:
+            gathered = [None] * dist.get_world_size(process_group)
+            dist.all_gather_object(gathered, intervals, group=process_group)
+            all_intervals = [iv for part in gathered for iv in part]
+        else:
+            all_intervals = intervals
+        if not all_intervals:
+            if batch is not None:
+                batch.close()
+            return []
+        try:
+            if independent:
+                groups = [(s, e, [i]) for i, (s, e) in enumerate(intervals)]
+            else:
+                groups = group_intervals(all_intervals)
+            group_off = numpy.zeros(len(groups) + 1, dtype=numpy.int64)
+            group_off[1:] = numpy.cumsum([g[1] - g[0] for g in groups])
+            total = int(group_off[-1])
+            # destination row of every local chunk inside the concatenated groups
+            starts = numpy.array([g[0] for g in groups], dtype=numpy.int64)
+            if independent:
+                dest = group_off[:-1].copy()
+            else:
+                local_starts = numpy.array([iv[0] for iv in intervals], dtype=numpy.int64)
+                gi = numpy.searchsorted(starts, local_starts, side='right') - 1
+                dest = group_off[gi] + (local_starts - starts[gi]) if len(intervals) else numpy.zeros(0, numpy.int64)
+            acc = torch.zeros((total, 4), dtype=torch.float64, device=dev)
+            cov = torch.zeros(total, dtype=torch.int32, device=dev)
+            if batch is not None:
+                d_chunks = torch.empty((batch.pack.total_reference, 4), dtype=torch.float64, device=dev)
+                batch.chunk_values([int(it.apx.reverse_complement) for it in items],
+                                   self.normalization_event_length, d_chunks.data_ptr(), stream)
+                batch.scatter_add(d_chunks.data_ptr(), dest, acc.data_ptr(), cov.data_ptr(), stream)
+            if dist is not None and not independent:
+                dist.all_reduce(acc, group=process_group)  # the one exchange step (estimator.py:228-231)
+                dist.all_reduce(cov, group=process_group)
+            ref_codes = numpy.concatenate([_ref_codes(reference[g[0]:g[1]]) for g in groups])
+            d_ref = torch.as_tensor(ref_codes, device=dev)
+            out = torch.empty_like(acc)
+            dtw.posterior(dev.index, acc.data_ptr(), d_ref.data_ptr(), group_off, self.kmer_model.get_k(),
+                          self.snp_prior, out.data_ptr(), stream)
+            probabilities = out.cpu().numpy()
+            coverage = cov.cpu().numpy().astype(int)
+            self.last_stats = {'launches': (batch.launch_count if batch is not None else 0) + 1,
+                               'groups': len(groups), 'positions': total}
+        finally:
+            if batch is not None:
+                batch.close()
+        return [Chunk(g[0], g[1], probabilities[group_off[i]:group_off[i + 1]].copy(),
+                      coverage[group_off[i]:group_off[i + 1]].copy()) for i, g in enumerate(groups)]
+
+
+def _device(kmer_model):
+    import torch
+    if not torch.cuda.is_available():
+        raise dtw.NadavcaCudaError('no CUDA device available: nadavca_b200 has no CPU fallback')
+    dev = torch.device('cuda', kmer_model.device)
+    torch.cuda.set_device(dev)
+    return dev
+
+
+def _dist(process_group):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and (process_group is not None or dist.get_world_size() > 1):
+        return dist
+    return None

@@ -1,0 +1,60 @@
+"""Read container and host-side signal normalisation (reference nadavca/read.py).
+
+fast5 parsing needs h5py / ont formats and is out of scope; reads are built with
+``Read.from_arrays`` or by ``nadavca_b200.synthetic``.  Normalisation and the spline tweak stay on the host and use
+the same numpy / scipy calls as the reference, so the kernels see identical inputs.
+"""
+import numpy
+from scipy import interpolate
+
+
+class Read:
+    def __init__(self):
+        self.raw_signal = None
+        self.normalized_signal = None
+        self.tweaked_normalized_signal = None
+        self.strand = None
+        self.fastq = None
+        self.sequence_to_signal_mapping = None
+        self.sequence = None
+
+    @staticmethod
+    def from_arrays(raw_signal, sequence, sequence_to_signal_mapping, name='read'):
+        """Build a read from its three ingredients (read.py:10-17): raw samples, basecalled bases and the
+        base index -> sample index map of the basecaller."""
+        read = Read()
+        read.raw_signal = numpy.asarray(raw_signal)
+        read.sequence = numpy.array(list(sequence)) if isinstance(sequence, str) else numpy.asarray(sequence)
+        read.sequence_to_signal_mapping = dict(sequence_to_signal_mapping)
+        seq = ''.join(read.sequence)
+        read.fastq = '@{}\n{}\n+\n{}\n'.format(name, seq, 'I' * len(seq))
+        return read
+
+    @staticmethod
+    def load_from_fast5(filename, basecall_group, segmentation_group='Analyses/Segmentation_000'):
+        raise NotImplementedError(
+            'fast5 loading is host I/O outside the scope of nadavca_b200 (h5py is not available here); '
+            'build reads with Read.from_arrays(raw_signal, sequence, sequence_to_signal_mapping)')
+
+    @staticmethod
+    def normalize_reads(reads):
+        """One median / MAD pooled over all given reads, clipped to +-5 (read.py:67-81)."""
+        values = numpy.concatenate([numpy.asarray(read.raw_signal, dtype=float) for read in reads]) \
+            if len(reads) else numpy.zeros(0)
+        shift = float(numpy.median(values))
+        scale = float(numpy.median(abs(values - shift)))
+        for read in reads:
+            read.normalized_signal = numpy.clip((read.raw_signal - shift) / scale, -5, 5)
+
+    def tweak_signal_normalization(self, alignment, expected_means):
+        """Cubic smoothing spline from observed event means to expected levels (read.py:83-94)."""
+        data = []
+        for event, expected_mean in zip(alignment, expected_means):
+            mean = numpy.mean(self.normalized_signal[event[0]: event[1]])
+            if abs(expected_mean - mean) <= 1:
+                data.append((mean, expected_mean))
+        data.sort()
+        means = [d[0] for d in data]
+        expected = [d[1] for d in data]
+        spline = interpolate.splrep(means, expected, s=len(means))
+        self.tweaked_normalized_signal = interpolate.splev(self.normalized_signal, spline)
