@@ -36,7 +36,7 @@ def random_case(rng, k, cp, n, bw, mel, sparse=False, homopolymer=False):
                         np.arange(n)], axis=1)
     anchors[:, 0] = np.maximum.accumulate(anchors[:, 0])
     if sparse:
-        keep = np.sort(rng.choice(n, size=max(2, n // 4), replace=False))
+        keep = np.sort(rng.choice(n, size=min(n, max(2, n // 4)), replace=False))
         keep[0], keep[-1] = 0, n - 1
         anchors = anchors[np.unique(keep)]
     cb = rng.integers(0, 4, size=rng.integers(0, cp + 1))

@@ -1,0 +1,225 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI / Python drop-in) against the CPU oracle on the same
+seeded inputs.  Bars: alignment events and bands bit-exact (ints); log-likelihoods within LL_RTOL relative
+(north_star allows 1e-5; the fp64 kernels are held to 1e-9)."""
+import numpy as np
+import pytest
+
+from conftest import make_case
+
+pytestmark = pytest.mark.gpu
+
+LL_RTOL = 1e-9
+LL_ATOL = 1e-9
+
+SIG = [0.1, -0.1, 0.2, 1.1, 0.9, 1.0, 2.1, 1.9, 2.2, 3.0, 3.1, 2.9]
+ANC = [[0, 0], [3, 1], [6, 2], [9, 3]]
+
+
+@pytest.fixture(scope='module')
+def toy(lib_built):
+    from nadavca_b200.dtw import KmerModel
+    return KmerModel(1, 0, 4, [0, 1, 2, 3], [.5] * 4)
+
+
+def test_known_answers_refine(toy):
+    """Known-answer vectors produced by the compiled reference."""
+    from nadavca_b200 import dtw
+    for flag in (True, False):
+        out = dtw.refine_alignment(signal=SIG, reference=[0, 1, 2, 3], context_before=[], context_after=[],
+                                   approximate_alignment=ANC, bandwidth=3, min_event_length=2, kmer_model=toy,
+                                   model_transitions=flag)
+        assert out == [[0, 3], [3, 6], [6, 9], [9, 11]]
+    out = dtw.refine_alignment(signal=SIG, reference=[0, 0, 1, 1], context_before=[], context_after=[],
+                               approximate_alignment=ANC, bandwidth=3, min_event_length=2, kmer_model=toy,
+                               model_transitions=True)
+    assert out == [[0, 2], [2, 4], [4, 6], [6, 8]]
+    out = dtw.refine_alignment(signal=SIG[:3], reference=[0, 1, 2, 3], context_before=[], context_after=[],
+                               approximate_alignment=[[0, 0]], bandwidth=3, min_event_length=2, kmer_model=toy,
+                               model_transitions=True)
+    assert out == []
+
+
+def test_known_answers_log_likelihoods(toy):
+    from nadavca_b200 import dtw
+    ll = dtw.estimate_log_likelihoods(signal=SIG, reference=[0, 1, 2, 3], context_before=[], context_after=[],
+                                      approximate_alignment=ANC, bandwidth=3, min_event_length=2, kmer_model=toy,
+                                      model_wobbling=True)
+    np.testing.assert_allclose(ll[0], [-0.013043763389, -4.261977157088, -16.055214132595, -35.692998888034],
+                               rtol=1e-10)
+    np.testing.assert_allclose(ll[3], [-20.042425824037, -7.636074636067, -2.296276451577, -0.013043763389],
+                               rtol=1e-10)
+    ll = dtw.estimate_log_likelihoods(signal=SIG, reference=[0, 1, 2, 3], context_before=[], context_after=[],
+                                      approximate_alignment=ANC, bandwidth=3, min_event_length=2, kmer_model=toy,
+                                      model_wobbling=False)
+    np.testing.assert_allclose(ll[0], [-0.500222199981, -1.982921519971, -7.528306532021, -19.725561807744],
+                               rtol=1e-10)
+
+
+def assert_same_path(ev, case, bw, mel, om, flag, exact):
+    """Events must equal the oracle's bit for bit.  Only when `exact` is False -- inputs with EXACT mathematical
+    ties between posterior cells (homopolymer runs longer than k give consecutive rows with identical emissions;
+    zero-length events; a 1-mer model), where the reference's own argmax is decided by its last-ulp rounding noise
+    -- a different path is accepted if it is feasible and its max-product score under the ORACLE's posterior rows
+    equals the oracle path's score to 1e-9."""
+    from oracle import oracle as orc
+    want, dbg = orc.refine_alignment(case[2], case[3], case[4], case[5], case[6], bw, mel, om, flag, debug=True)
+    if len(want) == 0:
+        assert ev is None
+        return True
+    assert ev is not None
+    if ev.tolist() == want:
+        return True
+    assert not exact, 'alignment differs from the oracle'
+    bs, be = dbg['bs'], dbg['be']
+    off = np.concatenate([[0], np.cumsum(be - bs + 1)])
+    post = dbg['prefix'] + dbg['suffix']
+
+    def score(events):
+        events = np.asarray(events)
+        if flag:
+            cols = events.reshape(-1)
+            mins = [mel if r % 2 == 0 else 0 for r in range(len(cols) - 1)]
+        else:
+            cols = np.concatenate([events[:, 0], events[-1:, 1]])
+            assert np.array_equal(events[1:, 0], events[:-1, 1])
+            mins = [mel] * (len(cols) - 1)
+        total = 0.0
+        for r, c in enumerate(cols):
+            assert bs[r] <= c <= be[r]
+            if r:
+                assert c - cols[r - 1] >= mins[r - 1]
+            total += post[off[r] + c - bs[r]]
+        return total
+    a, b = score(ev), score(want)
+    assert abs(a - b) <= 1e-9 * max(1.0, abs(b)), (a, b)
+    return False
+
+
+def _compare_batch(rng, cases, k, cp, mel, bw, mean, sigma, exact=True, tie_cases=()):
+    """Run a ragged batch through the GPU and every read through the oracle."""
+    from nadavca_b200 import dtw
+    from oracle import oracle as orc
+    gm = dtw.KmerModel(k, cp, 4, mean, sigma)
+    om = orc.OracleModel(k, cp, 4, mean, sigma, 'port')
+    sigs = [c[2] for c in cases]
+    refs = [c[3] for c in cases]
+    cbs = [c[4] for c in cases]
+    cas = [c[5] for c in cases]
+    ancs = [c[6] for c in cases]
+    with dtw.Batch(gm, sigs, refs, cbs, cas, ancs, bw, mel) as batch:
+        bands = batch.bands()
+        for (bs, be), c in zip(bands, cases):
+            obs, obe = orc.band_bounds(c[6], len(c[2]), len(c[3]), bw)
+            assert np.array_equal(bs, obs) and np.array_equal(be, obe)
+        for flag in (False, True):
+            batch.refine(flag)
+            events, status = batch.events()
+            for ci, (ev, st, c) in enumerate(zip(events, status, cases)):
+                assert_same_path(ev, c, bw, mel, om, flag, exact and ci not in tie_cases)
+                assert (ev is None) == (st == 1)
+            batch.estimate(flag)
+            lls, status = batch.log_likelihoods()
+            for ll, c in zip(lls, cases):
+                want = np.array(orc.estimate_log_likelihoods(c[2], c[3], c[4], c[5], c[6], bw, mel, om, flag))
+                finite = np.isfinite(want)
+                assert np.array_equal(np.isfinite(ll), finite)
+                np.testing.assert_allclose(ll[finite], want[finite], rtol=LL_RTOL, atol=LL_ATOL)
+        exp = gm.get_expected_signal_batch(refs, cbs, cas)
+        for e, c in zip(exp, cases):
+            assert e.tolist() == om.get_expected_signal(c[3], c[4], c[5])
+
+
+@pytest.mark.parametrize('mel', [0, 1, 2, 3])
+@pytest.mark.parametrize('k,cp', [(1, 0), (3, 1), (4, 2), (6, 2)])
+def test_random_batches_match_oracle(lib_built, k, cp, mel):
+    rng = np.random.default_rng(100 * k + mel)
+    bw = int(rng.integers(3, 20))
+    mean = rng.normal(0, 1.2, size=4 ** k)
+    sigma = rng.uniform(0.2, 0.6, size=4 ** k)
+    cases = []
+    for i in range(12):
+        n = int(rng.integers(1, 90)) if i else 1
+        c = make_case(rng, k, cp, n, bw, mel, sparse=i % 3 == 1, homopolymer=i % 4 == 2)
+        cases.append((mean, sigma) + c[2:])
+    # exact ties between posterior cells are structural in the toy corners (zero-length events, 1-mer model) and in
+    # the cases built with a homopolymer run longer than k (i % 4 == 2)
+    _compare_batch(rng, cases, k, cp, mel, bw, mean, sigma, exact=(mel > 0 and k > 1),
+                   tie_cases=[i for i in range(12) if i % 4 == 2])
+
+
+def test_no_path_and_mixed_status(lib_built):
+    """A read whose band cannot hold min_event_length samples per base has no path (reference returns [])."""
+    rng = np.random.default_rng(5)
+    k, cp, mel, bw = 2, 1, 3, 2
+    mean = rng.normal(0, 1, size=16)
+    sigma = np.full(16, 0.4)
+    good = make_case(rng, k, cp, 20, bw, mel, spacing=8)
+    sig = rng.normal(0, 1, 12)
+    bad = (mean, sigma, sig, rng.integers(0, 4, 10), [], [], np.array([[0, 0], [11, 9]]))
+    cases = [(mean, sigma) + good[2:], bad, (mean, sigma) + make_case(rng, k, cp, 33, bw, mel, spacing=8)[2:]]
+    _compare_batch(rng, cases, k, cp, mel, bw, mean, sigma)
+
+
+def test_default_model_read_matches_oracle(default_model):
+    """Shipped 6-mer model, default bandwidth 150 / min_event_length 2, one ~300-base synthetic read per strand."""
+    from nadavca_b200 import dtw, synthetic
+    from nadavca_b200.read import Read
+    from oracle import oracle as orc
+    km = default_model
+    om = orc.OracleModel(km.get_k(), km.get_central_position(), 4, km.mean, km.sigma, 'port')
+    genome = synthetic.make_genome(3000, seed=1)
+    reads = [synthetic.make_read(genome, km, i, n_bases=300, strand=s, substitution_rate=0.02)
+             for i, s in enumerate('+-')]
+    Read.normalize_reads(reads)
+    aligner = synthetic.SyntheticAligner(genome)
+    args = []
+    for r in reads:
+        apx = aligner.get_signal_alignment(r, 150)
+        s0, s1 = apx.signal_range
+        ref = orc.to_numerical(apx.reference_part)
+        a, b = apx.read_sequence_range
+        cb = orc.to_numerical(r.sequence[a - 2:a])
+        ca = orc.to_numerical(r.sequence[b:b + 3])
+        args.append((r.normalized_signal[s0:s1], ref, cb, ca, apx.alignment))
+    with dtw.Batch(km, *[list(x) for x in zip(*args)], 150, 2) as batch:
+        for flag in (True, False):
+            batch.refine(flag)
+            events, _ = batch.events()
+            for ev, a in zip(events, args):
+                assert ev.tolist() == orc.refine_alignment(*a, 150, 2, om, flag)
+        batch.estimate(True)
+        lls, _ = batch.log_likelihoods()
+        for ll, a in zip(lls, args):
+            want = np.array(orc.estimate_log_likelihoods(*a, 150, 2, om, True))
+            np.testing.assert_allclose(ll, want, rtol=LL_RTOL)
+        counts = batch.cell_counts(True)
+        want = {key: 0 for key in counts}
+        for a in args:
+            c = orc.count_cells(a[4], len(a[0]), len(a[1]), 150, 6, 2)
+            for key in want:
+                want[key] += c[key]
+        assert counts == want
+
+
+def test_workspace_waves_give_identical_results(default_model):
+    """Forcing the batch through several waves (small workspace limit) must not change any result."""
+    from nadavca_b200 import dtw
+    rng = np.random.default_rng(11)
+    k, cp, mel, bw = 3, 1, 2, 10
+    mean = rng.normal(0, 1.2, size=64)
+    sigma = rng.uniform(0.2, 0.6, size=64)
+    cases = [make_case(rng, k, cp, int(rng.integers(20, 60)), bw, mel) for _ in range(9)]
+    gm = dtw.KmerModel(k, cp, 4, mean, sigma)
+    lists = [[c[i] for c in cases] for i in (2, 3, 4, 5, 6)]
+    out = []
+    for limit in (0, 60_000):
+        with dtw.Batch(gm, *lists, bw, mel, workspace_limit=limit) as batch:
+            batch.refine(True)
+            ev, _ = batch.events()
+            batch.estimate(True)
+            ll, _ = batch.log_likelihoods()
+            out.append(([e.copy() for e in ev], [x.copy() for x in ll]))
+    for a, b in zip(out[0][0], out[1][0]):
+        assert np.array_equal(a, b)
+    for a, b in zip(out[0][1], out[1][1]):
+        assert np.array_equal(a, b)
