@@ -118,6 +118,15 @@ int32_t *nvb_batch_d_events(nvb_batch *batch);
 int32_t *nvb_batch_d_status(nvb_batch *batch);
 /* number of kernels launched by this batch object so far (bench.py reports it as gpu_launches) */
 int64_t nvb_batch_launch_count(const nvb_batch *batch);
+/* per-stage device timing with CUDA events recorded on the run's stream (measurement only; no reference
+ * counterpart).  Stages: 0 forward/backward rows, 1 path + traceback, 2 no-SNP total, 3 SNP loop. */
+#define NVB_N_STAGES 4
+int nvb_batch_enable_timing(nvb_batch *batch, int on);
+/* synchronises the device; ms / launches are accumulated since the last call (then reset) */
+int nvb_batch_get_timing(nvb_batch *batch, double ms[NVB_N_STAGES], int64_t launches[NVB_N_STAGES]);
+/* sustained FP64 FMA issue rate of `device` in FMA/s (a register-resident DFMA loop on every SM, best of 3);
+ * the denominator of the ALU roofline reported by bench.py */
+int nvb_measure_fp64_fma_rate(int device, double *fma_per_second);
 
 /* ---- estimator post-processing on the device (nadavca/estimator.py) ------------------------------------------ */
 /* (n,3) alignment table of get_refined_alignment (estimator.py:187-195):

@@ -67,6 +67,9 @@ SIGNATURES = {
     'nvb_batch_d_events': (ctypes.c_void_p, [ctypes.c_void_p]),
     'nvb_batch_d_status': (ctypes.c_void_p, [ctypes.c_void_p]),
     'nvb_batch_launch_count': (ctypes.c_int64, [ctypes.c_void_p]),
+    'nvb_batch_enable_timing': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    'nvb_batch_get_timing': (ctypes.c_int, [ctypes.c_void_p, c_f64p, c_i64p]),
+    'nvb_measure_fp64_fma_rate': (ctypes.c_int, [ctypes.c_int, c_f64p]),
     'nvb_batch_get_alignment_table': (ctypes.c_int, [ctypes.c_void_p, c_i64p, c_i64p, c_i64p, c_i32p, c_i64p]),
     'nvb_batch_chunk_values': (ctypes.c_int, [ctypes.c_void_p, c_i32p, ctypes.c_double, ctypes.c_void_p,
                                               ctypes.c_void_p]),
@@ -148,6 +151,32 @@ class ReadsPack:
         self.anchors, self.anchor_off = pack(alignments, np.int32, width=2)
         self.bandwidth = int(bandwidth)
         self.min_event_length = int(min_event_length)
+        self._make_struct()
+
+    @classmethod
+    def from_packed(cls, signal, signal_off, reference, reference_off, context_before, context_before_off,
+                    context_after, context_after_off, anchors, anchor_off, bandwidth, min_event_length):
+        """Wrap already packed CSR arrays WITHOUT copying (they may live in pinned host memory); dtypes must be
+        float64 / int32 / int64 as in the C struct."""
+        self = cls.__new__(cls)
+        self.n_reads = len(signal_off) - 1
+        for name, arr, dtype in (('signal', signal, np.float64), ('signal_off', signal_off, np.int64),
+                                 ('reference', reference, np.int32), ('reference_off', reference_off, np.int64),
+                                 ('context_before', context_before, np.int32),
+                                 ('context_before_off', context_before_off, np.int64),
+                                 ('context_after', context_after, np.int32),
+                                 ('context_after_off', context_after_off, np.int64),
+                                 ('anchors', anchors, np.int32), ('anchor_off', anchor_off, np.int64)):
+            if arr.dtype != dtype or not arr.flags['C_CONTIGUOUS']:
+                raise ValueError('{} must be a contiguous {} array'.format(name, np.dtype(dtype).name))
+            setattr(self, name, arr)
+        self.bandwidth = int(bandwidth)
+        self.min_event_length = int(min_event_length)
+        self._make_struct()
+        return self
+
+    def _make_struct(self):
+        n = self.n_reads
         self.struct = NvbReads(
             n, ptr(self.signal, ctypes.c_double), ptr(self.signal_off, ctypes.c_int64),
             ptr(self.reference, ctypes.c_int32), ptr(self.reference_off, ctypes.c_int64),

@@ -92,7 +92,26 @@ struct nvb_batch {
   int64_t ws_limit = 0;
   int64_t launches = 0;
   BatchDev dev{};
+  // optional per-stage timing
+  bool timing = false;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> timed;  // (stage, (start, stop))
+  ~nvb_batch() {
+    for (auto &t : timed) { cudaEventDestroy(t.second.first); cudaEventDestroy(t.second.second); }
+  }
 };
+
+namespace {
+// RAII helper: records a start/stop event pair around one kernel launch when timing is enabled
+struct StageTimer {
+  nvb_batch *b; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr; int stage;
+  StageTimer(nvb_batch *batch, int stage_, cudaStream_t stream) : b(batch), st(stream), stage(stage_) {
+    if (b->timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+  }
+  ~StageTimer() {
+    if (b->timing) { cudaEventRecord(e1, st); b->timed.push_back({stage, {e0, e1}}); }
+  }
+};
+}  // namespace
 
 extern "C" {
 
@@ -355,9 +374,15 @@ int nvb_batch_refine(nvb_batch *b, int model_transitions, void *stream) {
   if (rc) return rc;
   CU(b->d_events.alloc((size_t)2 * b->total_ref));
   for (const Wave &w : waves) {
-    nvbk_sweep(b->model->dev, b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->d_prefix.p, b->d_suffix.p, st);
-    nvbk_path(b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->d_prefix.p, b->d_suffix.p, b->d_dp.p, b->d_dp_base.p,
-              b->d_events.p, b->d_status.p, st);
+    {
+      StageTimer t(b, 0, st);
+      nvbk_sweep(b->model->dev, b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->d_prefix.p, b->d_suffix.p, st);
+    }
+    {
+      StageTimer t(b, 1, st);
+      nvbk_path(b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->d_prefix.p, b->d_suffix.p, b->d_dp.p,
+                b->d_dp_base.p, b->d_events.p, b->d_status.p, st);
+    }
     b->launches += 2;
   }
   CU(cudaGetLastError());
@@ -380,11 +405,21 @@ int nvb_batch_estimate(nvb_batch *b, int model_wobbling, void *stream) {
   nvbk_fill_status(b->dev, b->d_status.p, b->d_ll.p, M.alphabet, st);
   b->launches++;
   for (const Wave &w : waves) {
-    nvbk_sweep(M, b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->d_prefix.p, b->d_suffix.p, st);
-    nvbk_no_snp(M, b->dev, w.b0, w.b1, b->d_mat_base.p, b->d_prefix.p, b->d_suffix.p, b->d_ll.p, st);
-    if (nvbk_snp(M, b->dev, model_wobbling, w.b0, w.b1, b->ref_off[w.b0], b->ref_off[w.b1], b->d_mat_base.p,
-                 b->d_prefix.p, b->d_suffix.p, b->d_ll.p, st))
-      return fail(NVB_EINVAL, "SNP kernel configuration not supported");
+    {
+      StageTimer t(b, 0, st);
+      nvbk_sweep(M, b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->d_prefix.p, b->d_suffix.p, st);
+    }
+    {
+      StageTimer t(b, 2, st);
+      nvbk_no_snp(M, b->dev, w.b0, w.b1, b->d_mat_base.p, b->d_prefix.p, b->d_suffix.p, b->d_ll.p, st);
+    }
+    int snp_rc;
+    {
+      StageTimer t(b, 3, st);
+      snp_rc = nvbk_snp(M, b->dev, model_wobbling, w.b0, w.b1, b->ref_off[w.b0], b->ref_off[w.b1],
+                        b->d_mat_base.p, b->d_prefix.p, b->d_suffix.p, b->d_ll.p, st);
+    }
+    if (snp_rc) return fail(NVB_EINVAL, "SNP kernel configuration not supported");
     b->launches += 3;
   }
   CU(cudaGetLastError());
@@ -462,6 +497,50 @@ double *nvb_batch_d_log_likelihoods(nvb_batch *b) { return b && b->have_ll ? b->
 int32_t *nvb_batch_d_events(nvb_batch *b) { return b && b->have_events ? b->d_events.p : nullptr; }
 int32_t *nvb_batch_d_status(nvb_batch *b) { return b ? b->d_status.p : nullptr; }
 int64_t nvb_batch_launch_count(const nvb_batch *b) { return b ? b->launches : 0; }
+
+int nvb_batch_enable_timing(nvb_batch *b, int on) {
+  if (!b) return fail(NVB_EINVAL, "NULL batch");
+  b->timing = on != 0;
+  return NVB_OK;
+}
+
+int nvb_batch_get_timing(nvb_batch *b, double ms[NVB_N_STAGES], int64_t launches[NVB_N_STAGES]) {
+  if (!b || !ms || !launches) return fail(NVB_EINVAL, "NULL argument");
+  CU(cudaSetDevice(b->model->device));
+  CU(cudaDeviceSynchronize());
+  for (int i = 0; i < NVB_N_STAGES; i++) { ms[i] = 0; launches[i] = 0; }
+  for (auto &t : b->timed) {
+    float x = 0;
+    CU(cudaEventElapsedTime(&x, t.second.first, t.second.second));
+    ms[t.first] += x;
+    launches[t.first] += 1;
+    cudaEventDestroy(t.second.first);
+    cudaEventDestroy(t.second.second);
+  }
+  b->timed.clear();
+  return NVB_OK;
+}
+
+int nvb_measure_fp64_fma_rate(int device, double *fma_per_second) {
+  if (!fma_per_second) return fail(NVB_EINVAL, "NULL argument");
+  if (nvb_device_count() <= device) return fail(NVB_ECUDA, "CUDA device %d not available", device);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  DevBuf<double> sink;
+  CU(sink.alloc(1));
+  const int blocks = prop.multiProcessorCount * 8, iters = 1 << 16;
+  nvbk_fp64_fma_probe(1 << 10, blocks, 0, sink.p);  // warm-up
+  double best = 0;
+  for (int rep = 0; rep < 3; rep++) {
+    float ms = nvbk_fp64_fma_probe(iters, blocks, 0, sink.p);
+    CU(cudaGetLastError());
+    double rate = 8.0 * iters * 256.0 * blocks / (ms * 1e-3);
+    best = std::max(best, rate);
+  }
+  *fma_per_second = best;
+  return NVB_OK;
+}
 
 int nvb_refine_alignment_batch(nvb_model *model, const nvb_reads *reads, int model_transitions, int32_t *events,
                                int32_t *status) {

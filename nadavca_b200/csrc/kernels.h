@@ -34,3 +34,6 @@ void nvbk_scatter_add(const BatchDev &B, const double *d_chunks, const int64_t *
 void nvbk_posterior(const double *d_ll, const int8_t *d_ref, const int64_t *d_group_off, int n_groups,
                     int64_t total, int k, double snp_prior, double *d_out, cudaStream_t st);
 void nvbk_fill_status(const BatchDev &B, int32_t *d_status, double *d_ll, int alphabet, cudaStream_t st);
+
+// microbench.cu
+float nvbk_fp64_fma_probe(int iters, int blocks, cudaStream_t st, double *d_sink);

@@ -95,10 +95,10 @@ class Batch:
     """A batch of reads resident in HBM (nvb_batch_* of the C ABI)."""
 
     def __init__(self, kmer_model, signals, references, contexts_before, contexts_after, alignments, bandwidth,
-                 min_event_length, workspace_limit=0):
+                 min_event_length, workspace_limit=0, pack=None):
         self.model = kmer_model
-        self.pack = ReadsPack(signals, references, contexts_before, contexts_after, alignments, bandwidth,
-                              min_event_length)
+        self.pack = pack if pack is not None else ReadsPack(signals, references, contexts_before, contexts_after,
+                                                            alignments, bandwidth, min_event_length)
         self.lib = _cabi.require_device()
         h = self.lib.nvb_batch_create(kmer_model.handle, ctypes.byref(self.pack.struct))
         if not h:
@@ -107,6 +107,12 @@ class Batch:
         if workspace_limit:
             _cabi.check(self.lib.nvb_batch_set_workspace_limit(self.handle, int(workspace_limit)),
                         'nvb_batch_set_workspace_limit')
+
+    @classmethod
+    def from_pack(cls, kmer_model, pack, workspace_limit=0):
+        """Batch over an existing ReadsPack (e.g. ReadsPack.from_packed over pinned host arrays)."""
+        return cls(kmer_model, None, None, None, None, None, pack.bandwidth, pack.min_event_length,
+                   workspace_limit=workspace_limit, pack=pack)
 
     def close(self):
         if getattr(self, 'handle', None) is not None:
@@ -131,8 +137,12 @@ class Batch:
         return self.pack.n_reads
 
     def set_signals(self, signals):
-        flat = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.float64) for s in signals])
-                                    if len(signals) else np.zeros(0), dtype=np.float64)
+        """Replace the signal values; `signals` is a list of per-read arrays or one flat float64 array."""
+        if isinstance(signals, np.ndarray) and signals.ndim == 1 and signals.dtype == np.float64:
+            flat = np.ascontiguousarray(signals)
+        else:
+            flat = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.float64) for s in signals])
+                                        if len(signals) else np.zeros(0), dtype=np.float64)
         if flat.size != self.pack.total_signal:
             raise ValueError('replacement signals must keep the batch layout')
         _cabi.check(self.lib.nvb_batch_set_signal(self.handle, _cabi.ptr(flat, ctypes.c_double)),
@@ -215,6 +225,27 @@ class Batch:
     @property
     def launch_count(self):
         return int(self.lib.nvb_batch_launch_count(self.handle))
+
+    STAGES = ('rows', 'path', 'no_snp', 'snp')
+
+    def enable_timing(self, on=True):
+        _cabi.check(self.lib.nvb_batch_enable_timing(self.handle, int(on)), 'nvb_batch_enable_timing')
+
+    def timing(self):
+        """Per-stage device milliseconds / launches accumulated since the last call (CUDA events)."""
+        ms = np.zeros(4, dtype=np.float64)
+        cnt = np.zeros(4, dtype=np.int64)
+        _cabi.check(self.lib.nvb_batch_get_timing(self.handle, _cabi.ptr(ms, ctypes.c_double),
+                                                  _cabi.ptr(cnt, ctypes.c_int64)), 'nvb_batch_get_timing')
+        return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(self.STAGES)}
+
+
+def measure_fp64_fma_rate(device=0):
+    """FP64 FMA/s of the device (nvb_measure_fp64_fma_rate)."""
+    lib = _cabi.require_device()
+    out = ctypes.c_double(0)
+    _cabi.check(lib.nvb_measure_fp64_fma_rate(int(device), ctypes.byref(out)), 'nvb_measure_fp64_fma_rate')
+    return out.value
 
 
 def _stream(stream):

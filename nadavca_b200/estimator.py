@@ -247,62 +247,86 @@ class ProbabilityEstimator:
         with one call per read, estimate_snps.py:63-68) and returns one Chunk per aligned read in input order.
         Otherwise chunks are summed per overlap group; with an initialised torch.distributed `process_group` the
         reads given to each rank are that rank's shard and the per-position sums are all-reduced over NCCL."""
-        import torch
         items, batch = self._run_estimate(reference, reads)
-        dev = _device(self.kmer_model)
-        stream = torch.cuda.current_stream()
-        dist = _dist(process_group)
-        intervals = [tuple(it.apx.reference_range) for it in items]
-        if dist is not None and not independent:
-            gathered = [None] * dist.get_world_size(process_group)
-            dist.all_gather_object(gathered, intervals, group=process_group)
-            all_intervals = [iv for part in gathered for iv in part]
-        else:
-            all_intervals = intervals
-        if not all_intervals:
-            if batch is not None:
-                batch.close()
-            return []
         try:
-            if independent:
-                groups = [(s, e, [i]) for i, (s, e) in enumerate(intervals)]
-            else:
-                groups = group_intervals(all_intervals)
-            group_off = numpy.zeros(len(groups) + 1, dtype=numpy.int64)
-            group_off[1:] = numpy.cumsum([g[1] - g[0] for g in groups])
-            total = int(group_off[-1])
-            # destination row of every local chunk inside the concatenated groups
-            starts = numpy.array([g[0] for g in groups], dtype=numpy.int64)
-            if independent:
-                dest = group_off[:-1].copy()
-            else:
-                local_starts = numpy.array([iv[0] for iv in intervals], dtype=numpy.int64)
-                gi = numpy.searchsorted(starts, local_starts, side='right') - 1
-                dest = group_off[gi] + (local_starts - starts[gi]) if len(intervals) else numpy.zeros(0, numpy.int64)
-            acc = torch.zeros((total, 4), dtype=torch.float64, device=dev)
-            cov = torch.zeros(total, dtype=torch.int32, device=dev)
-            if batch is not None:
-                d_chunks = torch.empty((batch.pack.total_reference, 4), dtype=torch.float64, device=dev)
-                batch.chunk_values([int(it.apx.reverse_complement) for it in items],
-                                   self.normalization_event_length, d_chunks.data_ptr(), stream)
-                batch.scatter_add(d_chunks.data_ptr(), dest, acc.data_ptr(), cov.data_ptr(), stream)
-            if dist is not None and not independent:
-                dist.all_reduce(acc, group=process_group)  # the one exchange step (estimator.py:228-231)
-                dist.all_reduce(cov, group=process_group)
-            ref_codes = numpy.concatenate([_ref_codes(reference[g[0]:g[1]]) for g in groups])
-            d_ref = torch.as_tensor(ref_codes, device=dev)
-            out = torch.empty_like(acc)
-            dtw.posterior(dev.index, acc.data_ptr(), d_ref.data_ptr(), group_off, self.kmer_model.get_k(),
-                          self.snp_prior, out.data_ptr(), stream)
+            stage = self.posterior_stage(batch, [int(it.apx.reverse_complement) for it in items],
+                                         [tuple(it.apx.reference_range) for it in items], reference, independent,
+                                         process_group)
+            if stage is None:
+                return []
+            groups, group_off, out, cov = stage
             probabilities = out.cpu().numpy()
             coverage = cov.cpu().numpy().astype(int)
             self.last_stats = {'launches': (batch.launch_count if batch is not None else 0) + 1,
-                               'groups': len(groups), 'positions': total}
+                               'groups': len(groups), 'positions': int(group_off[-1])}
         finally:
             if batch is not None:
                 batch.close()
         return [Chunk(g[0], g[1], probabilities[group_off[i]:group_off[i + 1]].copy(),
                       coverage[group_off[i]:group_off[i + 1]].copy()) for i, g in enumerate(groups)]
+
+    def posterior_stage(self, batch, reverse, intervals, reference, independent=False, process_group=None,
+                        plan=None):
+        """Device half of estimate_probabilities after the raw log-likelihoods exist in `batch`: normalise / flip,
+        scatter-add into the concatenated groups, all-reduce (consensus over several ranks), posterior stencil.
+        Returns (groups, group_off, probabilities tensor (total,4), coverage tensor (total,)) or None.  `plan` (from
+        ``plan_groups``) can be reused between calls with the same intervals."""
+        import torch
+        dev = _device(self.kmer_model)
+        stream = torch.cuda.current_stream()
+        dist = _dist(process_group)
+        if plan is None:
+            plan = self.plan_groups(intervals, reference, independent, process_group)
+        if plan is None:
+            return None
+        groups, group_off, dest, d_ref = plan
+        total = int(group_off[-1])
+        acc = torch.zeros((total, 4), dtype=torch.float64, device=dev)
+        cov = torch.zeros(total, dtype=torch.int32, device=dev)
+        if batch is not None:
+            d_chunks = torch.empty((batch.pack.total_reference, 4), dtype=torch.float64, device=dev)
+            batch.chunk_values(reverse, self.normalization_event_length, d_chunks.data_ptr(), stream)
+            batch.scatter_add(d_chunks.data_ptr(), dest, acc.data_ptr(), cov.data_ptr(), stream)
+        if dist is not None and not independent:
+            dist.all_reduce(acc, group=process_group)  # the one exchange step (estimator.py:228-231)
+            dist.all_reduce(cov, group=process_group)
+        out = torch.empty_like(acc)
+        dtw.posterior(dev.index, acc.data_ptr(), d_ref.data_ptr(), group_off, self.kmer_model.get_k(),
+                      self.snp_prior, out.data_ptr(), stream)
+        return groups, group_off, out, cov
+
+    def plan_groups(self, intervals, reference, independent=False, process_group=None):
+        """Host planning of the overlap groups (estimator.py:205-220): (groups, group_off, dest rows of the local
+        chunks, device int8 reference codes) or None when no read aligned anywhere."""
+        import torch
+        dev = _device(self.kmer_model)
+        dist = _dist(process_group)
+        if dist is not None and not independent:
+            gathered = [None] * dist.get_world_size(process_group)
+            dist.all_gather_object(gathered, list(intervals), group=process_group)
+            all_intervals = [tuple(iv) for part in gathered for iv in part]
+        else:
+            all_intervals = list(intervals)
+        if not all_intervals:
+            return None
+        if independent:
+            groups = [(s, e, [i]) for i, (s, e) in enumerate(intervals)]
+        else:
+            groups = group_intervals(all_intervals)
+        group_off = numpy.zeros(len(groups) + 1, dtype=numpy.int64)
+        group_off[1:] = numpy.cumsum([g[1] - g[0] for g in groups])
+        starts = numpy.array([g[0] for g in groups], dtype=numpy.int64)
+        if independent:
+            dest = group_off[:-1].copy()
+        elif len(intervals):
+            local_starts = numpy.array([iv[0] for iv in intervals], dtype=numpy.int64)
+            gi = numpy.searchsorted(starts, local_starts, side='right') - 1
+            dest = group_off[gi] + (local_starts - starts[gi])
+        else:
+            dest = numpy.zeros(0, dtype=numpy.int64)
+        ref_codes = numpy.concatenate([_ref_codes(reference[g[0]:g[1]]) for g in groups])
+        d_ref = torch.as_tensor(ref_codes, device=dev)
+        return groups, group_off, dest, d_ref
 
 
 def _device(kmer_model):
