@@ -116,6 +116,9 @@ int nvb_batch_cell_counts(nvb_batch *batch, int model_wobbling, int64_t counts[4
 double *nvb_batch_d_log_likelihoods(nvb_batch *batch);
 int32_t *nvb_batch_d_events(nvb_batch *batch);
 int32_t *nvb_batch_d_status(nvb_batch *batch);
+/* debugging aid: the stored DP rows of read `read` after nvb_batch_estimate (plane 0 = prefix, 1 = suffix) as
+ * log-probabilities, packed band rows 0..n (cells = sum of band widths); the read must be in the last wave */
+int nvb_batch_debug_rows(nvb_batch *batch, int read, int plane, double *out_log, int64_t n_cells);
 /* number of kernels launched by this batch object so far (bench.py reports it as gpu_launches) */
 int64_t nvb_batch_launch_count(const nvb_batch *batch);
 /* per-stage device timing with CUDA events recorded on the run's stream (measurement only; no reference

@@ -67,6 +67,7 @@ SIGNATURES = {
     'nvb_batch_d_events': (ctypes.c_void_p, [ctypes.c_void_p]),
     'nvb_batch_d_status': (ctypes.c_void_p, [ctypes.c_void_p]),
     'nvb_batch_launch_count': (ctypes.c_int64, [ctypes.c_void_p]),
+    'nvb_batch_debug_rows': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_f64p, ctypes.c_int64]),
     'nvb_batch_enable_timing': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     'nvb_batch_get_timing': (ctypes.c_int, [ctypes.c_void_p, c_f64p, c_i64p]),
     'nvb_measure_fp64_fma_rate': (ctypes.c_int, [ctypes.c_int, c_f64p]),

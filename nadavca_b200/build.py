@@ -10,8 +10,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnadavca_b200.so")
-SOURCES = ["api.cu", "band.cu", "rows.cu", "snp.cu", "path.cu", "finalize.cu", "microbench.cu"]
-HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "nadavca_b200.h")]
+SOURCES = ["api.cu", "band.cu", "rows2.cu", "snp2.cu", "path.cu", "finalize.cu", "microbench.cu"]
+HEADERS = ["common.cuh", "dp2.cuh", "kernels.h", os.path.join("..", "..", "include", "nadavca_b200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
@@ -36,7 +36,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
+    extra = os.environ.get("NVB_EXTRA_FLAGS", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
         [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

@@ -87,7 +87,8 @@ struct nvb_batch {
   DevBuf<double> d_ll;
   bool have_events = false, have_ll = false;
   // workspace
-  DevBuf<double> d_prefix, d_suffix, d_dp;
+  DevBuf<double> d_pF, d_sF, d_dp;   // DP matrices: mantissa planes
+  DevBuf<int32_t> d_pX, d_sX;        // ... and exponent planes
   DevBuf<int64_t> d_mat_base, d_dp_base;
   int64_t ws_limit = 0;
   int64_t launches = 0;
@@ -223,7 +224,7 @@ int batch_init(nvb_batch *b, const nvb_reads *r) {
   int rc;
   if (n < 0) return fail(NVB_EINVAL, "n_reads < 0");
   if (r->bandwidth < 0 || r->min_event_length < 0) return fail(NVB_EINVAL, "bandwidth / min_event_length must be >= 0");
-  if (r->min_event_length > 1022) return fail(NVB_EINVAL, "min_event_length > 1022 is not supported");
+  if (r->min_event_length > 6) return fail(NVB_EINVAL, "min_event_length > 6 is not supported");
   if ((rc = check_offsets(r->signal_off, n, "signal"))) return rc;
   if ((rc = check_offsets(r->anchor_off, n, "anchor"))) return rc;
   if ((rc = upload_sequences(b, n, r->reference, r->reference_off, r->context_before, r->context_before_off,
@@ -286,7 +287,7 @@ int plan_waves(nvb_batch *b, int mode, bool need_dp, std::vector<Wave> &waves, s
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     // memory already held by this batch's workspace can be reused
-    free_b += (b->d_prefix.n + b->d_suffix.n + b->d_dp.n) * sizeof(double);
+    free_b += (b->d_pF.n + b->d_sF.n + b->d_dp.n) * sizeof(double) + (b->d_pX.n + b->d_sX.n) * sizeof(int32_t);
     limit = (int64_t)(free_b * 0.7);
   }
   const int n = b->n_reads;
@@ -299,7 +300,7 @@ int plan_waves(nvb_batch *b, int mode, bool need_dp, std::vector<Wave> &waves, s
     int j = i;
     while (j < n) {
       int64_t c = matrix_cells(b, j, mode), d = need_dp ? 2 * (int64_t)b->maxw[j] : 0;
-      int64_t bytes = ((cells + c) * 2 + (dp + d)) * (int64_t)sizeof(double);
+      int64_t bytes = (cells + c) * 2 * (int64_t)(sizeof(double) + sizeof(int32_t)) + (dp + d) * (int64_t)sizeof(double);
       if (bytes > limit && j > i) break;
       if (bytes > limit)
         return fail(NVB_ENOMEM, "read %d needs %lld bytes of DP workspace, limit is %lld", j, (long long)bytes, (long long)limit);
@@ -320,10 +321,11 @@ int prepare_workspace(nvb_batch *b, int mode, bool need_dp, std::vector<Wave> &w
   int64_t max_cells = 0, max_dp = 0;
   int rc = plan_waves(b, mode, need_dp, waves, mat_base, dp_base, max_cells, max_dp);
   if (rc) return rc;
-  if (b->d_prefix.alloc((size_t)max_cells) != cudaSuccess || b->d_suffix.alloc((size_t)max_cells) != cudaSuccess ||
+  if (b->d_pF.alloc((size_t)max_cells) != cudaSuccess || b->d_sF.alloc((size_t)max_cells) != cudaSuccess ||
+      b->d_pX.alloc((size_t)max_cells) != cudaSuccess || b->d_sX.alloc((size_t)max_cells) != cudaSuccess ||
       b->d_dp.alloc((size_t)max_dp) != cudaSuccess) {
     cudaGetLastError();
-    return fail(NVB_ENOMEM, "cannot allocate %lld bytes of DP workspace", (long long)((2 * max_cells + max_dp) * 8));
+    return fail(NVB_ENOMEM, "cannot allocate %lld bytes of DP workspace", (long long)(24 * max_cells + 8 * max_dp));
   }
   CU(upload(b->d_mat_base, mat_base.data(), mat_base.size(), st));
   CU(upload(b->d_dp_base, dp_base.data(), dp_base.size(), st));
@@ -376,11 +378,13 @@ int nvb_batch_refine(nvb_batch *b, int model_transitions, void *stream) {
   for (const Wave &w : waves) {
     {
       StageTimer t(b, 0, st);
-      nvbk_sweep(b->model->dev, b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->d_prefix.p, b->d_suffix.p, st);
+      if (nvbk_sweep2(b->model->dev, b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->d_pF.p, b->d_pX.p, b->d_sF.p,
+                      b->d_sX.p, st))
+        return fail(NVB_EINVAL, "min_event_length %d is not supported (maximum 6)", b->dev.mel);
     }
-    {
+    if (!getenv("NVB_DEBUG_SKIP_PATH")) {
       StageTimer t(b, 1, st);
-      nvbk_path(b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->d_prefix.p, b->d_suffix.p, b->d_dp.p,
+      nvbk_path(b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->d_pF.p, b->d_pX.p, b->d_sF.p, b->d_sX.p, b->d_dp.p,
                 b->d_dp_base.p, b->d_events.p, b->d_status.p, st);
     }
     b->launches += 2;
@@ -396,8 +400,7 @@ int nvb_batch_estimate(nvb_batch *b, int model_wobbling, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const ModelDev &M = b->model->dev;
   const int mode = model_wobbling ? NVB_MODE_WOBBLE : NVB_MODE_PLAIN;
-  if ((model_wobbling ? 2 * M.k + 2 : M.k + 1) > 32)
-    return fail(NVB_EINVAL, "k = %d is too large for the SNP kernel (needs 2k+2 <= 32 lanes)", M.k);
+  if (M.k + 2 > 32) return fail(NVB_EINVAL, "k = %d is too large for the SNP kernel (needs k+2 <= 32 lanes)", M.k);
   std::vector<Wave> waves;
   int rc = prepare_workspace(b, mode, false, waves, st);
   if (rc) return rc;
@@ -407,17 +410,19 @@ int nvb_batch_estimate(nvb_batch *b, int model_wobbling, void *stream) {
   for (const Wave &w : waves) {
     {
       StageTimer t(b, 0, st);
-      nvbk_sweep(M, b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->d_prefix.p, b->d_suffix.p, st);
+      if (nvbk_sweep2(M, b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->d_pF.p, b->d_pX.p, b->d_sF.p, b->d_sX.p, st))
+        return fail(NVB_EINVAL, "min_event_length %d is not supported (maximum 6)", b->dev.mel);
     }
     {
       StageTimer t(b, 2, st);
-      nvbk_no_snp(M, b->dev, w.b0, w.b1, b->d_mat_base.p, b->d_prefix.p, b->d_suffix.p, b->d_ll.p, st);
+      nvbk_no_snp2(M, b->dev, w.b0, w.b1, b->d_mat_base.p, b->d_pF.p, b->d_pX.p, b->d_sF.p, b->d_sX.p, b->d_ll.p,
+                   st);
     }
     int snp_rc;
     {
       StageTimer t(b, 3, st);
-      snp_rc = nvbk_snp(M, b->dev, model_wobbling, w.b0, w.b1, b->ref_off[w.b0], b->ref_off[w.b1],
-                        b->d_mat_base.p, b->d_prefix.p, b->d_suffix.p, b->d_ll.p, st);
+      snp_rc = nvbk_snp2(M, b->dev, model_wobbling, w.b0, w.b1, b->ref_off[w.b0], b->ref_off[w.b1],
+                         b->d_mat_base.p, b->d_pF.p, b->d_pX.p, b->d_sF.p, b->d_sX.p, b->d_ll.p, st);
     }
     if (snp_rc) return fail(NVB_EINVAL, "SNP kernel configuration not supported");
     b->launches += 3;
@@ -497,6 +502,23 @@ double *nvb_batch_d_log_likelihoods(nvb_batch *b) { return b && b->have_ll ? b->
 int32_t *nvb_batch_d_events(nvb_batch *b) { return b && b->have_events ? b->d_events.p : nullptr; }
 int32_t *nvb_batch_d_status(nvb_batch *b) { return b ? b->d_status.p : nullptr; }
 int64_t nvb_batch_launch_count(const nvb_batch *b) { return b ? b->launches : 0; }
+
+int nvb_batch_debug_rows(nvb_batch *b, int read, int plane, double *out_log, int64_t n_cells) {
+  if (!b || !out_log || read < 0 || read >= b->n_reads) return fail(NVB_EINVAL, "bad argument");
+  if (n_cells != b->cells[read] && n_cells != 2 * b->cells[read] - b->w0[read] - b->wn[read])
+    return fail(NVB_EINVAL, "read %d has %lld cells", read, (long long)b->cells[read]);
+  CU(cudaSetDevice(b->model->device));
+  CU(cudaDeviceSynchronize());
+  int64_t base = 0;
+  CU(cudaMemcpy(&base, b->d_mat_base.p + read, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  std::vector<double> f((size_t)n_cells);
+  std::vector<int32_t> x((size_t)n_cells);
+  CU(cudaMemcpy(f.data(), (plane ? b->d_sF.p : b->d_pF.p) + base, (size_t)n_cells * sizeof(double), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(x.data(), (plane ? b->d_sX.p : b->d_pX.p) + base, (size_t)n_cells * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n_cells; i++)
+    out_log[i] = f[i] > 0.0 ? log(f[i]) + x[i] * 0.6931471805599453 : -INFINITY;
+  return NVB_OK;
+}
 
 int nvb_batch_enable_timing(nvb_batch *b, int on) {
   if (!b) return fail(NVB_EINVAL, "NULL batch");

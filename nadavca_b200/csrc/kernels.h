@@ -6,22 +6,23 @@
 void nvbk_band(const BatchDev &B, int64_t *d_summary, cudaStream_t st);
 void nvbk_expected_signal(const ModelDev &M, const BatchDev &B, int64_t total, double *d_out, cudaStream_t st);
 
-// rows.cu: forward + backward banded rows for reads [b0,b1) (one warp per read and direction)
-void nvbk_sweep(const ModelDev &M, const BatchDev &B, int mode, int b0, int b1, const int64_t *d_mat_base,
-                double *d_prefix, double *d_suffix, cudaStream_t st);
+// rows2.cu: forward + backward banded rows for reads [b0,b1) (one warp per read and direction); rows are stored
+// as a mantissa plane (double) and an exponent plane (int32).  Returns -1 for an unsupported min_event_length.
+int nvbk_sweep2(const ModelDev &M, const BatchDev &B, int mode, int b0, int b1, const int64_t *d_mat_base,
+                double *pF, int32_t *pX, double *sF, int32_t *sX, cudaStream_t st);
 // no-SNP total (dtw.cpp:83-85) written into the reference-base column of out_ll
-void nvbk_no_snp(const ModelDev &M, const BatchDev &B, int b0, int b1, const int64_t *d_mat_base,
-                 const double *d_prefix, const double *d_suffix, double *d_out_ll, cudaStream_t st);
+void nvbk_no_snp2(const ModelDev &M, const BatchDev &B, int b0, int b1, const int64_t *d_mat_base, const double *pF,
+                  const int32_t *pX, const double *sF, const int32_t *sX, double *d_out_ll, cudaStream_t st);
 
-// snp.cu: the SNP re-run loop (dtw.cpp:93-129)
-int nvbk_snp(const ModelDev &M, const BatchDev &B, int wobbling, int b0, int b1, int64_t g0, int64_t g1,
-             const int64_t *d_mat_base, const double *d_prefix, const double *d_suffix, double *d_out_ll,
-             cudaStream_t st);
+// snp2.cu: the SNP re-run loop (dtw.cpp:93-129)
+int nvbk_snp2(const ModelDev &M, const BatchDev &B, int wobbling, int b0, int b1, int64_t g0, int64_t g1,
+              const int64_t *d_mat_base, const double *pF, const int32_t *pX, const double *sF, const int32_t *sX,
+              double *d_out_ll, cudaStream_t st);
 
 // path.cu: posterior rows, max-product path, traceback (dtw.cpp:199-227)
-void nvbk_path(const BatchDev &B, int mode, int b0, int b1, const int64_t *d_mat_base, double *d_prefix,
-               const double *d_suffix, double *d_dp, const int64_t *d_dp_base, int32_t *d_events,
-               int32_t *d_status, cudaStream_t st);
+void nvbk_path(const BatchDev &B, int mode, int b0, int b1, const int64_t *d_mat_base, const double *pF,
+               int32_t *pX, const double *sF, const int32_t *sX, double *d_dp, const int64_t *d_dp_base,
+               int32_t *d_events, int32_t *d_status, cudaStream_t st);
 
 // finalize.cu
 void nvbk_alignment_table(const BatchDev &B, const int32_t *d_events, const int32_t *d_status,

@@ -3,12 +3,13 @@
 // Replaces reference nadavca/dtw/dtw.cpp:199-227 with Node::operator* (node.cpp:23-29),
 // PathSearchingNode::NextRow / GetBestIndex / GetPrevious (node.cpp:39-91).
 //
-// One warp per read walks the rows in order.  A row's score is prefix + suffix (read coalesced from HBM); the
-// running "best predecessor over i' <= c - m" is an inclusive (max, first-argmax) scan along the row -- strict '>'
-// so the lowest index wins ties, index -1 while everything is log(0).  The back-pointer of a cell overwrites the
-// low 32 bits of that cell's slot in the prefix matrix (the prefix value is dead once the score is formed), so the
-// traceback needs no extra HBM.  Lane 0 then walks the back-pointers from the last row.
-#include "common.cuh"
+// One warp per read walks the rows in order.  A row's score is log(prefix * suffix), formed from the (mantissa,
+// exponent) planes written by rows2.cu (one log per cell, read coalesced from HBM); the running "best predecessor
+// over i' <= c - m" is an inclusive (max, first-argmax) scan along the row -- strict '>' so the lowest index wins
+// ties, index -1 while everything is log(0).  The back-pointer of a cell overwrites that cell's slot in the prefix
+// exponent plane (dead once the score is formed), so the traceback needs no extra HBM.  Lane 0 then walks the
+// back-pointers from the last row.
+#include "dp2.cuh"
 #include "kernels.h"
 
 namespace {
@@ -44,8 +45,9 @@ __device__ __forceinline__ void row_geom(const ReadView &v, int mode, int r, int
 }
 
 __global__ void __launch_bounds__(128) path_kernel(BatchDev B, int mode, int b0, int n_items, const int64_t *mat_base,
-                                                   double *prefix, const double *suffix, double *dp,
-                                                   const int64_t *dp_base, int32_t *events, int32_t *status) {
+                                                   const double *pF, int32_t *pX, const double *sF,
+                                                   const int32_t *sX, double *dp, const int64_t *dp_base,
+                                                   int32_t *events, int32_t *status) {
   const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * (blockDim.x >> 5) + wic;
   if (item >= n_items) return;
@@ -60,9 +62,10 @@ __global__ void __launch_bounds__(128) path_kernel(BatchDev B, int mode, int b0,
   }
   const double NINF = nvb_neg_inf();
   const int R = (mode == NVB_MODE_TRANS) ? 2 * n : n + 1;
-  double *P = prefix + mat_base[b];
-  const double *S = suffix + mat_base[b];
-  int32_t *bp = reinterpret_cast<int32_t *>(P);
+  const double *PF = pF + mat_base[b];
+  const double *SF = sF + mat_base[b];
+  const int32_t *SX = sX + mat_base[b];
+  int32_t *bp = pX + mat_base[b];  // prefix exponents, overwritten cell by cell with back-pointers
   double *dp_prev = dp + dp_base[b];
   double *dp_cur = dp_prev + B.max_width[b];
 
@@ -71,9 +74,9 @@ __global__ void __launch_bounds__(128) path_kernel(BatchDev B, int mode, int b0,
   row_geom(v, mode, 0, s, e, off);
   for (int c = s + lane; c <= e; c += NVB_WARP) {  // dp[0] = PathSearchingNode(all_paths_sum[0]) (dtw.cpp:205)
     int64_t x = off + c - s;
-    double sc = P[x] + S[x];
+    double sc = log_ext(PF[x] * SF[x], bp[x] + SX[x]);
     __stcg(dp_prev + (c - s), sc);
-    bp[2 * x] = -1;
+    bp[x] = -1;
   }
   __syncwarp();
 
@@ -107,9 +110,9 @@ __global__ void __launch_bounds__(128) path_kernel(BatchDev B, int mode, int b0,
       if (!(x.v > carry.v)) x = carry;
       if (c <= e) {
         const int64_t k = off + c - s;
-        const double sc = P[k] + S[k];
+        const double sc = log_ext(PF[k] * SF[k], bp[k] + SX[k]);
         __stcg(dp_cur + (c - s), x.v + sc);
-        bp[2 * k] = x.i;
+        bp[k] = x.i;
       }
       carry.v = __shfl_sync(NVB_FULL, x.v, NVB_WARP - 1);
       carry.i = __shfl_sync(NVB_FULL, x.i, NVB_WARP - 1);
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(128) path_kernel(BatchDev B, int mode, int b0,
         if (r > 0) ev[2 * (r - 1) + 1] = bi;
         if (r + 1 < R) ev[2 * r] = bi;
       }
-      bi = __ldcg(bp + 2 * (off + bi - s));
+      bi = __ldcg(bp + (off + bi - s));
     }
     status[b] = 0;
   }
@@ -155,11 +158,11 @@ __global__ void __launch_bounds__(128) path_kernel(BatchDev B, int mode, int b0,
 
 }  // namespace
 
-void nvbk_path(const BatchDev &B, int mode, int b0, int b1, const int64_t *d_mat_base, double *d_prefix,
-               const double *d_suffix, double *d_dp, const int64_t *d_dp_base, int32_t *d_events,
-               int32_t *d_status, cudaStream_t st) {
+void nvbk_path(const BatchDev &B, int mode, int b0, int b1, const int64_t *d_mat_base, const double *pF,
+               int32_t *pX, const double *sF, const int32_t *sX, double *d_dp, const int64_t *d_dp_base,
+               int32_t *d_events, int32_t *d_status, cudaStream_t st) {
   const int n_items = b1 - b0;
   if (n_items <= 0) return;
-  path_kernel<<<(n_items + 3) / 4, 128, 0, st>>>(B, mode, b0, n_items, d_mat_base, d_prefix, d_suffix, d_dp,
-                                                 d_dp_base, d_events, d_status);
+  path_kernel<<<(n_items + 3) / 4, 128, 0, st>>>(B, mode, b0, n_items, d_mat_base, pF, pX, sF, sX, d_dp, d_dp_base,
+                                                 d_events, d_status);
 }

@@ -222,6 +222,16 @@ class Batch:
                                                    _cabi.ptr(d, ctypes.c_int64), ctypes.c_void_p(d_acc),
                                                    ctypes.c_void_p(d_cov), _stream(stream)), 'nvb_batch_scatter_add')
 
+    def debug_rows(self, read, plane, transitions=False):
+        """Stored DP rows of one read after estimate() as log-probabilities (plane 0 prefix, 1 suffix)."""
+        bs, be = self.bands()[read]
+        w = be - bs + 1
+        cells = int(2 * w.sum() - w[0] - w[-1]) if transitions else int(w.sum())
+        out = np.zeros(cells, dtype=np.float64)
+        _cabi.check(self.lib.nvb_batch_debug_rows(self.handle, int(read), int(plane),
+                                                  _cabi.ptr(out, ctypes.c_double), cells), 'nvb_batch_debug_rows')
+        return out
+
     @property
     def launch_count(self):
         return int(self.lib.nvb_batch_launch_count(self.handle))

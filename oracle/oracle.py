@@ -202,8 +202,9 @@ def refine_alignment(signal, reference, context_before, context_after, approxima
 
 
 def estimate_log_likelihoods(signal, reference, context_before, context_after, approximate_alignment, bandwidth,
-                             min_event_length, kmer_model, model_wobbling):
-    """EstimateLogLikelihoods (dtw.cpp:37-131) -> n x alphabet list of lists."""
+                             min_event_length, kmer_model, model_wobbling, debug=False):
+    """EstimateLogLikelihoods (dtw.cpp:37-131) -> n x alphabet list of lists.  debug=True (port only) also returns
+    dict(prefix, suffix) with the packed stored rows 0..n."""
     if kmer_model.backend == 'ref':
         return ref_module().estimate_log_likelihoods(
             signal=np.asarray(signal, dtype=float).tolist(), reference=list(map(int, reference)),
@@ -214,11 +215,17 @@ def estimate_log_likelihoods(signal, reference, context_before, context_after, a
     sig = np.ascontiguousarray(signal, dtype=np.float64)
     ref, cb, ca, anc = _i32(reference), _i32(context_before), _i32(context_after), _i32(approximate_alignment)
     out = np.zeros((ref.size, kmer_model.alphabet_size), dtype=np.float64)
+    dbg, args = None, [None, None]
+    if debug:
+        bs, be = band_bounds(approximate_alignment, sig.size, ref.size, bandwidth)
+        cells = int((be - bs + 1).sum())
+        dbg = {'prefix': np.zeros(cells), 'suffix': np.zeros(cells), 'bs': bs, 'be': be}
+        args = [_p(dbg['prefix'], ctypes.c_double), _p(dbg['suffix'], ctypes.c_double)]
     port_lib().nvo_estimate_log_likelihoods(
         kmer_model.handle, _p(sig, ctypes.c_double), sig.size, _p(ref, ctypes.c_int32), ref.size,
         _p(cb, ctypes.c_int32), cb.size, _p(ca, ctypes.c_int32), ca.size, _p(anc, ctypes.c_int32), anc.size // 2,
-        int(bandwidth), int(min_event_length), int(bool(model_wobbling)), _p(out, ctypes.c_double), None, None)
-    return out.tolist()
+        int(bandwidth), int(min_event_length), int(bool(model_wobbling)), _p(out, ctypes.c_double), *args)
+    return (out.tolist(), dbg) if debug else out.tolist()
 
 
 # ---- estimator glue, restated (reference nadavca/estimator.py) -----------------------------------------------
