@@ -293,6 +293,22 @@ def workload_config(args, reads_per_gpu):
 
 # ---- GPU arm ------------------------------------------------------------------------------------------------------
 
+def first_read_index(rank, reads_per_gpu):
+    """Weak scaling: rank r simulates (and owns) reads [r*R, (r+1)*R) of the seeded workload; no read is shared."""
+    return rank * reads_per_gpu
+
+
+def reduce_over_ranks(value, op, device):
+    """max / sum of a host scalar over all ranks (identity for a single process)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX if op == 'max' else dist.ReduceOp.SUM)
+    return float(t.item())
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -314,7 +330,7 @@ def run_ours(args):
 
     km = load_model()
     km._device = local_rank
-    genome, items = make_workload(km, args.reads, rank * args.reads, args.bases, args.genome, args.bandwidth)
+    genome, items = make_workload(km, args.reads, first_read_index(rank, args.reads), args.bases, args.genome, args.bandwidth)
     est = ProbabilityEstimator(km, None, cfg)
 
     lists = ([it['signal'] for it in items], [it['reference'] for it in items], [it['cb'] for it in items],
@@ -413,18 +429,11 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
 
     # ---- reductions over ranks -----------------------------------------------------------------------------------
-    def reduce(value, op):
-        if world == 1:
-            return value
-        t = torch.tensor([value], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=op)
-        return float(t.item())
-
-    ms_max = reduce(ms, dist.ReduceOp.MAX if world > 1 else None)
-    e2e_max = reduce(e2e_s, dist.ReduceOp.MAX if world > 1 else None)
-    samples_all = reduce(float(samples), dist.ReduceOp.SUM if world > 1 else None)
-    cells_all = reduce(float(total_cells), dist.ReduceOp.SUM if world > 1 else None)
-    launches_all = reduce(float(launches), dist.ReduceOp.SUM if world > 1 else None)
+    ms_max = reduce_over_ranks(ms, 'max', dev)
+    e2e_max = reduce_over_ranks(e2e_s, 'max', dev)
+    samples_all = reduce_over_ranks(float(samples), 'sum', dev)
+    cells_all = reduce_over_ranks(float(total_cells), 'sum', dev)
+    launches_all = reduce_over_ranks(float(launches), 'sum', dev)
 
     if rank == 0:
         value = samples_all * args.steps / (ms_max * 1e-3)

@@ -300,33 +300,61 @@ class ProbabilityEstimator:
         chunks, device int8 reference codes) or None when no read aligned anywhere."""
         import torch
         dev = _device(self.kmer_model)
-        dist = _dist(process_group)
-        if dist is not None and not independent:
-            gathered = [None] * dist.get_world_size(process_group)
-            dist.all_gather_object(gathered, list(intervals), group=process_group)
-            all_intervals = [tuple(iv) for part in gathered for iv in part]
-        else:
-            all_intervals = list(intervals)
-        if not all_intervals:
+        host = plan_groups_host(intervals, independent, process_group)
+        if host is None:
             return None
-        if independent:
-            groups = [(s, e, [i]) for i, (s, e) in enumerate(intervals)]
-        else:
-            groups = group_intervals(all_intervals)
-        group_off = numpy.zeros(len(groups) + 1, dtype=numpy.int64)
-        group_off[1:] = numpy.cumsum([g[1] - g[0] for g in groups])
-        starts = numpy.array([g[0] for g in groups], dtype=numpy.int64)
-        if independent:
-            dest = group_off[:-1].copy()
-        elif len(intervals):
-            local_starts = numpy.array([iv[0] for iv in intervals], dtype=numpy.int64)
-            gi = numpy.searchsorted(starts, local_starts, side='right') - 1
-            dest = group_off[gi] + (local_starts - starts[gi])
-        else:
-            dest = numpy.zeros(0, dtype=numpy.int64)
+        groups, group_off, dest = host
         ref_codes = numpy.concatenate([_ref_codes(reference[g[0]:g[1]]) for g in groups])
         d_ref = torch.as_tensor(ref_codes, device=dev)
         return groups, group_off, dest, d_ref
+
+
+def plan_groups_host(intervals, independent=False, process_group=None):
+    """Pure host half of ``plan_groups`` (no device access, so it runs under the gloo backend in the CPU tests):
+    the overlap groups over the reads of ALL ranks, the concatenated row offset of every group and, for each LOCAL
+    read, the row of the concatenated accumulator its chunk is added at.  In consensus mode over several ranks the
+    (start, end) intervals are exchanged with one all_gather_object; `independent` needs no exchange."""
+    dist = _dist(process_group)
+    if dist is not None and not independent:
+        gathered = [None] * dist.get_world_size(process_group)
+        dist.all_gather_object(gathered, [tuple(map(int, iv)) for iv in intervals], group=process_group)
+        all_intervals = [tuple(iv) for part in gathered for iv in part]
+    else:
+        all_intervals = [tuple(iv) for iv in intervals]
+    if not all_intervals:
+        return None
+    if independent:
+        groups = [(s, e, [i]) for i, (s, e) in enumerate(intervals)]
+    else:
+        groups = group_intervals(all_intervals)
+    group_off = numpy.zeros(len(groups) + 1, dtype=numpy.int64)
+    group_off[1:] = numpy.cumsum([g[1] - g[0] for g in groups])
+    starts = numpy.array([g[0] for g in groups], dtype=numpy.int64)
+    if independent:
+        dest = group_off[:-1].copy()
+    elif len(intervals):
+        local_starts = numpy.array([iv[0] for iv in intervals], dtype=numpy.int64)
+        gi = numpy.searchsorted(starts, local_starts, side='right') - 1
+        dest = group_off[gi] + (local_starts - starts[gi])
+    else:
+        dest = numpy.zeros(0, dtype=numpy.int64)
+    return groups, group_off, dest
+
+
+def shard_reads(work, world_size):
+    """Deal reads to ranks by longest-processing-time-first on a per-read work estimate (DP cells ~ bases x band
+    width): returns a list of `world_size` index lists, each in ascending read order.  Reads are independent units
+    (estimator.py:201-204), so this is the whole multi-GPU partitioning; ties and equal work fall back to a
+    round-robin deal."""
+    work = numpy.asarray(work, dtype=numpy.float64)
+    order = numpy.argsort(-work, kind='stable')
+    load = numpy.zeros(world_size)
+    shards = [[] for _ in range(world_size)]
+    for idx in order:
+        r = int(numpy.argmin(load))
+        shards[r].append(int(idx))
+        load[r] += work[idx]
+    return [sorted(s) for s in shards]
 
 
 def _device(kmer_model):

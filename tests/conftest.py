@@ -52,3 +52,56 @@ def make_case(rng, k, cp, n, bw, mel, sparse=False, homopolymer=False, spacing=6
     cb = rng.integers(0, 4, size=rng.integers(0, cp + 1))
     ca = rng.integers(0, 4, size=rng.integers(0, k - cp))
     return mean, sigma, sig, ref, cb, ca, anchors
+
+
+GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
+
+
+class Golden:
+    """Flat npz written by oracle/make_golden.py; keys look like 'case/field'."""
+
+    def __init__(self, name):
+        self.data = np.load(os.path.join(GOLDEN_DIR, name), allow_pickle=False)
+
+    def __getitem__(self, key):
+        return self.data[key]
+
+    def case(self, tag):
+        pre = tag + '/'
+        return {k[len(pre):]: self.data[k] for k in self.data.files if k.startswith(pre)}
+
+
+@pytest.fixture(scope='session')
+def golden_dp():
+    return Golden('dp_cases.npz')
+
+
+@pytest.fixture(scope='session')
+def golden_estimator():
+    return Golden('estimator_cases.npz')
+
+
+def golden_reads(golden):
+    """Rebuild the stored synthetic reads of estimator_cases.npz (raw signal, sequence, mapping, truth)."""
+    from nadavca_b200.read import Read
+    reads = []
+    for i in range(int(golden['n_reads'])):
+        seq = golden['read%d/sequence' % i]
+        mapping = golden['read%d/mapping' % i]
+        read = Read.from_arrays(golden['read%d/raw_signal' % i], seq, {b: int(s) for b, s in enumerate(mapping)},
+                                name='golden_%d' % i)
+        start, n, reverse, flank = (int(x) for x in golden['read%d/truth' % i])
+        read.truth = {'start': start, 'n': n, 'reverse': bool(reverse), 'flank': flank}
+        reads.append(read)
+    return reads
+
+
+GOLDEN_CONFIG = dict(bandwidth=30, snp_prior_probability=0.001, min_event_length=2, model_wobbling=True,
+                     model_transitions=True, tweak_signal_normalization=True, normalization_event_length=10)
+
+
+@pytest.fixture(scope='session')
+def default_model_host():
+    """The shipped 6-mer model described on the host (no CUDA needed until its device handle is used)."""
+    from nadavca_b200.kmer_model import KmerModel
+    return KmerModel.load_from_hdf5(os.path.join(ROOT, 'nadavca_b200', 'default', 'kmer_model.hdf5'))

@@ -1,0 +1,122 @@
+"""CPU suite, part 4: the N>1 host logic under torch.distributed (gloo, world_size 2, 127.0.0.1).
+
+The data path has one exchange step only in consensus mode (estimator.py:226-231: per-position sum of the reads'
+log-likelihood chunks).  Here two CPU ranks each own a shard of the reads (shard_reads), plan the overlap groups
+with one all_gather_object (plan_groups_host), add their chunks into the concatenated accumulator at the planned
+rows, all-reduce it, and must reproduce the single-process grouping, coverage and sums of the reference algorithm
+(the oracle's estimate_probabilities keeps the reference's order; a different summation order is allowed 1e-12)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _make_chunks(seed=3):
+    rng = np.random.default_rng(seed)
+    # three overlap groups, a touching pair (400..450 | 450..520: '>=' opens a new group) and a single
+    intervals = [(0, 80), (40, 130), (120, 200), (60, 100), (300, 360), (330, 400), (400, 450), (450, 520),
+                 (470, 540), (700, 760), (10, 50)]
+    values = [rng.normal(-2, 1, size=(e - s, 4)) for s, e in intervals]
+    return intervals, values
+
+
+def _single_process(intervals, values):
+    from nadavca_b200.estimator import group_intervals
+    groups = group_intervals(intervals)
+    out = []
+    for start, end, members in groups:
+        acc = np.zeros((end - start, 4))
+        cov = np.zeros(end - start, dtype=np.int64)
+        for i in sorted(members, key=lambda j: intervals[j]):
+            s, e = intervals[i]
+            acc[s - start:e - start] += values[i]
+            cov[s - start:e - start] += 1
+        out.append((start, end, acc, cov))
+    return out
+
+
+def _worker(rank, world, port, result_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from nadavca_b200.estimator import plan_groups_host, shard_reads
+        intervals, values = _make_chunks()
+        work = [e - s for s, e in intervals]
+        mine = shard_reads(work, world)[rank]
+        local_iv = [intervals[i] for i in mine]
+        groups, group_off, dest = plan_groups_host(local_iv, independent=False, process_group=dist.group.WORLD)
+        total = int(group_off[-1])
+        acc = torch.zeros((total, 4), dtype=torch.float64)
+        cov = torch.zeros(total, dtype=torch.int32)
+        for d, i in zip(dest, mine):
+            n = intervals[i][1] - intervals[i][0]
+            acc[d:d + n] += torch.from_numpy(values[i])
+            cov[d:d + n] += 1
+        dist.all_reduce(acc)
+        dist.all_reduce(cov)
+        # independent mode needs no exchange: planning must not communicate and keeps local order
+        g2, off2, dest2 = plan_groups_host(local_iv, independent=True, process_group=dist.group.WORLD)
+        assert len(g2) == len(local_iv) and dest2.tolist() == off2[:-1].tolist()
+        np.savez(os.path.join(result_dir, 'rank%d.npz' % rank), acc=acc.numpy(), cov=cov.numpy(),
+                 group_off=group_off, ranges=np.array([(g[0], g[1]) for g in groups]), mine=np.array(mine))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_consensus_reduce_two_ranks_gloo(tmp_path):
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    intervals, values = _make_chunks()
+    want = _single_process(intervals, values)
+    res = [np.load(os.path.join(str(tmp_path), 'rank%d.npz' % r)) for r in range(world)]
+    # every read is owned by exactly one rank
+    assert sorted(np.concatenate([r['mine'] for r in res]).tolist()) == list(range(len(intervals)))
+    for r in res:
+        assert r['ranges'].tolist() == [[s, e] for s, e, _, _ in want]
+        for gi, (s, e, acc, cov) in enumerate(want):
+            a, b = r['group_off'][gi], r['group_off'][gi + 1]
+            assert b - a == e - s
+            np.testing.assert_allclose(r['acc'][a:b], acc, rtol=1e-12, atol=1e-12)
+            assert np.array_equal(r['cov'][a:b], cov)
+    assert np.array_equal(res[0]['acc'], res[1]['acc'])
+    # the touching pair opened a new group
+    ranges = res[0]['ranges'].tolist()
+    assert any(ranges[i][1] == ranges[i + 1][0] for i in range(len(ranges) - 1))
+
+
+def _bench_rank_worker(rank, world, port, result_dir):
+    """bench.py's weak-scaling partition: rank r simulates reads [r*R, (r+1)*R) -- disjoint and deterministic."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import bench
+        t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+        assert bench.reduce_over_ranks(t.item(), 'max', None) == float(world)
+        assert bench.reduce_over_ranks(t.item(), 'sum', None) == world * (world + 1) / 2
+        first = bench.first_read_index(rank, 5)
+        np.save(os.path.join(result_dir, 'first%d.npy' % rank), np.array([first]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bench_rank_helpers_gloo(tmp_path):
+    world = 2
+    mp.spawn(_bench_rank_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    firsts = [int(np.load(os.path.join(str(tmp_path), 'first%d.npy' % r))[0]) for r in range(world)]
+    assert firsts == [0, 5]

@@ -1,0 +1,202 @@
+"""CPU suite, part 2: host-side logic of the drop-in (no GPU, no oracle compute): model file reader, packing,
+overlap groups, sharding, alignment contract, config handling, cell/byte accounting used by bench.py."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CONFIG, ROOT, golden_reads
+
+
+def test_hdf5_mini_reads_shipped_model(default_model_host):
+    """kmer_model.hdf5 without h5py: 4096 6-mers, central_pos 2, constant sd."""
+    km = default_model_host
+    assert (km.get_k(), km.get_central_position(), km.get_alphabet_size()) == (6, 2, 4)
+    assert km.mean.shape == (4096,) and km.sigma.shape == (4096,)
+    assert np.all(km.sigma == 0.3328800486427912)
+    assert abs(km.mean.min() + 3.178) < 1e-3 and abs(km.mean.max() - 2.831) < 1e-3
+    from nadavca_b200.kmer_model import kmer_to_id
+    assert kmer_to_id('AAAAAA') == 0 and kmer_to_id('TTTTTT') == 4095 and kmer_to_id('ACGTAC') == 0b000110110001
+
+
+def test_genome_helpers():
+    from nadavca_b200.genome import Genome
+    assert Genome.to_numerical('ACGTTG').tolist() == [0, 1, 2, 3, 3, 2]
+    assert ''.join(Genome.reverse_complement('AACGT')) == 'ACGTT'
+    assert ''.join(Genome.reverse_complement(np.array(list('TTGA')))) == 'TCAA'
+    with pytest.raises(KeyError):
+        Genome.to_numerical('ACGN')
+    fq = Genome.create_from_fastq_string('@r1\nACGT\n+\nIIII\n')
+    assert ''.join(fq[0].bases) == 'ACGT'
+
+
+def test_fasta_loader(tmp_path):
+    from nadavca_b200.genome import Genome
+    p = tmp_path / 'x.fa'
+    p.write_text('>chr1 test\nACGT\nTTAA\n>chr2\nGG\n')
+    gs = Genome.load_from_fasta(str(p))
+    assert [g.description for g in gs] == ['>chr1 test', '>chr2']
+    assert ''.join(gs[0].bases) == 'ACGTTTAA' and ''.join(gs[1].bases) == 'GG'
+
+
+def test_group_intervals_touching_chunks_split():
+    """estimator.py:216 uses '>=': a chunk starting exactly at the running end opens a new group."""
+    from nadavca_b200.estimator import group_intervals
+    iv = [(100, 200), (0, 50), (40, 90), (90, 100), (150, 260), (300, 310)]
+    groups = group_intervals(iv)
+    assert [(g[0], g[1]) for g in groups] == [(0, 90), (90, 100), (100, 260), (300, 310)]
+    assert [sorted(g[2]) for g in groups] == [[1, 2], [3], [0, 4], [5]]
+    assert group_intervals([]) == []
+    # a contained interval does not shorten the group
+    assert [(g[0], g[1]) for g in group_intervals([(0, 100), (10, 20), (99, 120)])] == [(0, 120)]
+
+
+def test_plan_groups_host_consensus_and_independent():
+    from nadavca_b200.estimator import plan_groups_host
+    iv = [(10, 30), (20, 50), (50, 60)]
+    groups, off, dest = plan_groups_host(iv, independent=False)
+    assert [(g[0], g[1]) for g in groups] == [(10, 50), (50, 60)]
+    assert off.tolist() == [0, 40, 50] and dest.tolist() == [0, 10, 40]
+    groups, off, dest = plan_groups_host(iv, independent=True)
+    assert off.tolist() == [0, 20, 50, 60] and dest.tolist() == [0, 20, 50]
+    assert plan_groups_host([], independent=False) is None
+
+
+def test_shard_reads_balances_work():
+    from nadavca_b200.estimator import shard_reads
+    rng = np.random.default_rng(0)
+    work = rng.integers(1000, 3000, size=203).astype(float)
+    for world in (1, 2, 4, 8):
+        shards = shard_reads(work, world)
+        assert sorted(i for s in shards for i in s) == list(range(203))
+        loads = [work[s].sum() for s in shards]
+        assert max(loads) - min(loads) <= work.max()
+        assert all(s == sorted(s) for s in shards)
+
+
+def test_reads_pack_layout_and_validation():
+    from nadavca_b200._cabi import ReadsPack
+    pack = ReadsPack([[0.5, 1.5, 2.5], [], [1.0]], [[0, 1], [], [3]], [[], [2], []], [[1], [], []],
+                     [[[0, 0], [2, 1]], np.zeros((0, 2)), [[0, 0]]], 7, 2)
+    assert pack.n_reads == 3
+    assert pack.signal_off.tolist() == [0, 3, 3, 4] and pack.signal.dtype == np.float64
+    assert pack.reference_off.tolist() == [0, 2, 2, 3] and pack.reference.dtype == np.int32
+    assert pack.context_before_off.tolist() == [0, 0, 1, 1] and pack.context_after_off.tolist() == [0, 1, 1, 1]
+    assert pack.anchor_off.tolist() == [0, 2, 2, 3] and pack.anchors.tolist() == [0, 0, 2, 1, 0, 0]
+    assert (pack.struct.n_reads, pack.struct.bandwidth, pack.struct.min_event_length) == (3, 7, 2)
+    assert pack.total_reference == 3 and pack.total_signal == 4
+    with pytest.raises(ValueError):
+        ReadsPack([[1.0]], [[0]], [[]], [[]], [[1, 2, 3]], 1, 1)      # anchors must be pairs
+    with pytest.raises(ValueError):
+        ReadsPack([[1.0]], [[0], [1]], [[]], [[]], [[[0, 0]]], 1, 1)  # ragged argument lists
+    again = ReadsPack.from_packed(pack.signal, pack.signal_off, pack.reference, pack.reference_off,
+                                  pack.context_before, pack.context_before_off, pack.context_after,
+                                  pack.context_after_off, pack.anchors, pack.anchor_off, 7, 2)
+    assert again.signal is pack.signal and again.n_reads == 3
+    with pytest.raises(ValueError):
+        ReadsPack.from_packed(pack.signal.astype(np.float32), pack.signal_off, pack.reference, pack.reference_off,
+                              pack.context_before, pack.context_before_off, pack.context_after,
+                              pack.context_after_off, pack.anchors, pack.anchor_off, 7, 2)
+
+
+def test_chunk_contract():
+    from nadavca_b200.estimator import Chunk
+    a, b, c = Chunk(5, 9, np.zeros((4, 4))), Chunk(5, 7, np.zeros((2, 4))), Chunk(1, 20, np.zeros((19, 4)))
+    assert sorted([a, b, c]) == [c, b, a]
+    assert a.coverage.tolist() == [1, 1, 1, 1]
+    out = io.StringIO()
+    Chunk.print_head(out)
+    Chunk(1, 3, np.array([[.25] * 4, [1, 0, 0, 0]]), np.array([2, 3])).print(out, 'ACGT')
+    lines = out.getvalue().splitlines()
+    assert lines[0] == 'index\tbase\tcoverage\tA\tC\tG\tT'
+    assert lines[1] == '1\tC\t2\t' + '\t'.join(['0.2500000000000000'] * 4)
+    assert lines[2].startswith('2\tG\t3\t1.0000000000000000\t0.0')
+
+
+def test_config_loading(tmp_path):
+    from nadavca_b200 import defaults
+    cfg = defaults.load_config()
+    assert cfg == dict(bandwidth=150, snp_prior_probability=0.001, min_event_length=2, model_wobbling=True,
+                       model_transitions=True, tweak_signal_normalization=True, normalization_event_length=10)
+    assert defaults.load_config(dict(cfg, bandwidth=30))['bandwidth'] == 30
+    with pytest.raises(KeyError):
+        defaults.load_config({'bandwidth': 3})
+    with pytest.raises(FileNotFoundError):
+        defaults.load_config(str(tmp_path / 'missing.yaml'))
+
+
+def test_synthetic_aligner_contract(golden_estimator):
+    """Layout of ApproximateSignalAlignment (alignment.py:142-186) on both strands."""
+    from nadavca_b200 import synthetic
+    from nadavca_b200.genome import Genome
+    from nadavca_b200.read import Read
+    genome = golden_estimator['genome']
+    reads = golden_reads(golden_estimator)
+    Read.normalize_reads(reads)
+    aligner = synthetic.SyntheticAligner(genome)
+    for r in reads:
+        apx = aligner.get_signal_alignment(r, 30)
+        n = apx.reference_range[1] - apx.reference_range[0]
+        assert apx.alignment[0][1] == 0 and apx.alignment[-1][1] == n - 1
+        assert np.all(np.diff(apx.alignment[:, 1]) > 0) and np.all(np.diff(apx.alignment[:, 0]) >= 0)
+        s0, s1 = apx.signal_range
+        assert 0 <= s0 < s1 <= len(r.normalized_signal)
+        assert apx.alignment[0][0] == min(30, apx.alignment[0][0] + s0)  # first anchor sits `bandwidth` in
+        part = genome[apx.reference_range[0]:apx.reference_range[1]]
+        if apx.reverse_complement:
+            part = Genome.reverse_complement(part)
+        assert np.array_equal(apx.reference_part, part) and len(part) == n
+        a, b = apx.read_sequence_range
+        assert b - a >= n  # anchored bases of the read span the reference part (substitutions never add bases)
+    assert aligner.get_signal_alignment(Read(), 30) is None
+
+
+def test_cigar_base_mapping():
+    from nadavca_b200.alignment import base_mapping_from_cigar, parse_cigar
+    assert parse_cigar('3S10M2D4M1I') == [(3, 'S'), (10, 'M'), (2, 'D'), (4, 'M'), (1, 'I')]
+    ref = np.array(list('AACCGGTTAC'))
+    read = np.array(list('TACCGTTT'))  # 1S 4M 1D 2M 1S against ref[1:]
+    m = base_mapping_from_cigar('1S4M1D2M1S', 1, read, ref, False)
+    assert m.tolist() == [[1, 1], [2, 2], [3, 3], [4, 4], [5, 6], [6, 7]]
+    with pytest.raises(ValueError):
+        base_mapping_from_cigar('3X', 0, read, ref, False)
+
+
+def test_read_normalisation_and_tweak_match_reference(golden_estimator):
+    """Read.normalize_reads == the reference's (stored normalised signals); the tweak is the same scipy call."""
+    from nadavca_b200.read import Read
+    reads = golden_reads(golden_estimator)
+    Read.normalize_reads(reads)
+    for i, r in enumerate(reads):
+        assert np.array_equal(r.normalized_signal, golden_estimator['read%d/normalized_signal' % i])
+        assert r.normalized_signal.min() >= -5 and r.normalized_signal.max() <= 5
+    with pytest.raises(NotImplementedError):
+        Read.load_from_fast5('x.fast5', 'Analyses/Basecall_1D_000')
+
+
+def test_band_stats_matches_oracle_counts(golden_dp):
+    """bench.py's cell accounting == the oracle's count_cells on the same bands."""
+    import bench
+    from oracle import oracle as orc
+    for tag in ['model6_0', 'model6_1', 'rnd09']:
+        c = golden_dp.case(tag)
+        k, cp, bw, mel = (int(x) for x in c['params'])
+        n, N = len(c['reference']), len(c['signal'])
+        bs, be = orc.band_bounds(c['anchors'], N, n, bw)
+        cells, nbytes = bench.band_stats([(bs, be)], k, cp, True)
+        want = orc.count_cells(c['anchors'], N, n, bw, k, cp)
+        assert cells['refine_plain'] == want['refine_plain']
+        assert cells['estimate_fb'] == want['estimate_fb']
+        assert cells['estimate_snp'] == want['estimate_snp']
+        assert all(v > 0 for v in nbytes.values())
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under nadavca_b200/ may import or execute it."""
+    pkg = os.path.join(ROOT, 'nadavca_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for name in files:
+            if name.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, name), errors='replace').read()
+                assert 'import oracle' not in text and 'from oracle' not in text and 'oracle/' not in text, name
