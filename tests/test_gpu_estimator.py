@@ -1,0 +1,178 @@
+"""GPU parity, API level: the drop-in Python surface (ProbabilityEstimator / estimate_snps / align_signal) on the
+B200 kernels against (a) the golden outputs of the reference's own estimator.py and (b) the oracle, plus
+size-independent properties at the full BASELINE read size.
+
+Tolerances (north_star: alignments bit-exact, log-likelihoods / probabilities <= 1e-5 relative):
+  alignment tables, coverage, group ranges : exact
+  normalised log-likelihood chunks          : rtol 1e-7 (atol 1e-9: entries that are exactly 0 in the reference)
+  SNP posterior probabilities               : rtol 1e-6, atol 1e-12
+"""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CONFIG, golden_reads
+
+pytestmark = pytest.mark.gpu
+
+CHUNK_RTOL, CHUNK_ATOL = 1e-7, 1e-9
+PROB_RTOL, PROB_ATOL = 1e-6, 1e-12
+
+
+def _setup(golden_estimator, default_model, tweak):
+    from nadavca_b200 import synthetic
+    from nadavca_b200.estimator import ProbabilityEstimator
+    from nadavca_b200.read import Read
+    genome = golden_estimator['genome']
+    reads = golden_reads(golden_estimator)
+    Read.normalize_reads(reads)
+    aligner = synthetic.SyntheticAligner(genome)
+    cfg = dict(GOLDEN_CONFIG, tweak_signal_normalization=bool(tweak))
+    return genome, reads, aligner, ProbabilityEstimator(default_model, aligner, cfg), cfg
+
+
+@pytest.mark.parametrize('tweak', [1, 0])
+def test_estimator_matches_reference_golden(golden_estimator, default_model, tweak):
+    g = golden_estimator
+    genome, reads, aligner, est, cfg = _setup(g, default_model, tweak)
+    pre = 'tweak%d/' % tweak
+    # path A: refined alignment tables, bit-exact
+    tables = est.get_refined_alignments(reads)
+    for i, res in enumerate(tables):
+        assert res is not None
+        assert np.array_equal(res[1], g[pre + 'read%d/alignment_table' % i]), i
+        assert res[1].dtype.kind == 'i' and res[1].shape[1] == 3
+    one = est.get_refined_alignment(reads[2])
+    assert np.array_equal(one[1], g[pre + 'read2/alignment_table'])
+    # path B: per-read normalised chunks
+    chunks = est.estimate_log_likelihood_chunks(genome, reads)
+    assert len(chunks) == len(reads)
+    for i, c in enumerate(chunks):
+        assert [c.start, c.end] == g[pre + 'read%d/chunk_range' % i].tolist()
+        np.testing.assert_allclose(c.values, g[pre + 'read%d/chunk_values' % i], rtol=CHUNK_RTOL, atol=CHUNK_ATOL)
+    # independent posteriors (estimate_snps.py:63-68) and the consensus groups (estimator.py:205-236)
+    ind = est.estimate_probabilities(genome, reads, independent=True)
+    for i, c in enumerate(ind):
+        np.testing.assert_allclose(c.values, g[pre + 'read%d/independent_probabilities' % i], rtol=PROB_RTOL,
+                                   atol=PROB_ATOL)
+        assert np.array_equal(c.coverage, np.ones(c.end - c.start, dtype=int))
+    groups = est.estimate_probabilities(genome, reads, independent=False)
+    assert len(groups) == int(g[pre + 'n_groups'])
+    for gi, c in enumerate(groups):
+        assert [c.start, c.end] == g[pre + 'group%d/range' % gi].tolist()
+        assert np.array_equal(c.coverage, g[pre + 'group%d/coverage' % gi])
+        np.testing.assert_allclose(c.values, g[pre + 'group%d/probabilities' % gi], rtol=PROB_RTOL, atol=PROB_ATOL)
+        np.testing.assert_allclose(c.values.sum(axis=1), 1.0, rtol=1e-12)
+
+
+def test_estimate_snps_api(golden_estimator, default_model):
+    """Public entry point with Read instances, a dict config and an injected aligner."""
+    import nadavca_b200
+    from nadavca_b200 import synthetic
+    g = golden_estimator
+    genome = g['genome']
+    aligner = synthetic.SyntheticAligner(genome)
+    for independent in (True, False):
+        reads = golden_reads(g)
+        out = nadavca_b200.estimate_snps(None, reads, reference=genome, config=GOLDEN_CONFIG,
+                                         kmer_model=default_model, independent=independent, aligner=aligner)
+        if independent:
+            assert len(out) == len(reads)
+            for i, c in enumerate(out):
+                np.testing.assert_allclose(c.values, g['tweak1/read%d/independent_probabilities' % i],
+                                           rtol=PROB_RTOL, atol=PROB_ATOL)
+        else:
+            assert [(c.start, c.end) for c in out] == [tuple(g['tweak1/group%d/range' % i]) for i in range(4)]
+            assert out == sorted(out)
+    assert nadavca_b200.estimate_snps(None, [], reference=genome, config='/nonexistent.yaml',
+                                      kmer_model=default_model, aligner=aligner) is None
+
+
+def test_align_signal_api_matches_oracle_loop(golden_estimator, default_model):
+    """align_signal's renormalisation rounds (align_signal.py:52-81) against the same loop driven by the oracle."""
+    import nadavca_b200
+    from nadavca_b200 import synthetic
+    from nadavca_b200.read import Read
+    from oracle import oracle as orc
+    from scipy.stats import linregress
+    g = golden_estimator
+    genome = g['genome']
+    aligner = synthetic.SyntheticAligner(genome)
+    km = default_model
+    got = list(nadavca_b200.align_signal(None, golden_reads(g), config=GOLDEN_CONFIG, kmer_model=km,
+                                         aligner=aligner, reference=genome))
+    om = orc.OracleModel(km.get_k(), km.get_central_position(), 4, km.mean, km.sigma, 'port')
+    est = orc.OracleEstimator(om, aligner, GOLDEN_CONFIG)
+    reads = golden_reads(g)
+    assert len(got) == len(reads)
+    for (read_out, res), read in zip(got, reads):
+        Read.normalize_reads([read])
+        apx, al = est.get_refined_alignment(read)
+        for r in range(3):
+            if r % 2 == 0:
+                expected = np.array(om.get_expected_signal(orc.to_numerical(apx.reference_part), [], []))
+                cut = read.normalized_signal[al[0][1]:al[-1][2]]
+                means = [np.mean(cut[s - al[0][1]:e - al[0][1]]) for _, s, e in al]
+                slope, intercept, _, _, _ = linregress(expected, means)
+                read.normalized_signal = (read.normalized_signal - intercept) / slope
+            else:
+                apx, al = est.get_refined_alignment(read)
+        assert res is not None
+        assert np.array_equal(res[1], al)
+        np.testing.assert_allclose(read_out.normalized_signal, read.normalized_signal, rtol=1e-12)
+
+
+def test_unaligned_reads_are_none(golden_estimator, default_model):
+    from nadavca_b200.read import Read
+    g = golden_estimator
+    genome, reads, aligner, est, cfg = _setup(g, default_model, 1)
+    stranger = Read.from_arrays(np.arange(50.0), 'ACGT' * 3, {i: 4 * i for i in range(12)})
+    Read.normalize_reads([stranger])
+    res = est.get_refined_alignments([reads[0], stranger, reads[1]])
+    assert res[1] is None and res[0] is not None and res[2] is not None
+    chunks = est.estimate_probabilities(genome, [stranger], independent=True)
+    assert chunks == []
+
+
+def test_full_size_reads_properties_and_oracle(default_model):
+    """BASELINE read size (~2000 bases, ~20k samples, bandwidth 150): two reads against the oracle, the rest
+    through size-independent properties."""
+    from nadavca_b200 import dtw, synthetic
+    from nadavca_b200.genome import Genome
+    from nadavca_b200.read import Read
+    from oracle import oracle as orc
+    km = default_model
+    genome = synthetic.make_genome(100_000, seed=4)
+    reads = [synthetic.make_read(genome, km, 900 + i, n_bases=1900 + 40 * i) for i in range(6)]
+    Read.normalize_reads(reads)
+    aligner = synthetic.SyntheticAligner(genome)
+    args = []
+    for r in reads:
+        apx = aligner.get_signal_alignment(r, 150)
+        s0, s1 = apx.signal_range
+        a, b = apx.read_sequence_range
+        args.append((r.normalized_signal[s0:s1], Genome.to_numerical(apx.reference_part),
+                     Genome.to_numerical(r.sequence[a - 2:a]), Genome.to_numerical(r.sequence[b:b + 3]),
+                     apx.alignment))
+    om = orc.OracleModel(6, 2, 4, km.mean, km.sigma, 'port')
+    with dtw.Batch(km, *[list(x) for x in zip(*args)], 150, 2) as batch:
+        for flag in (False, True):
+            batch.refine(flag)
+            events, status = batch.events()
+            assert np.all(status == 0)
+            for ev in events:
+                assert np.all(ev[:, 1] - ev[:, 0] >= 2) and np.all(ev[1:, 0] >= ev[:-1, 1])
+                if not flag:
+                    assert np.array_equal(ev[1:, 0], ev[:-1, 1])
+            for i in (0, 5):
+                assert events[i].tolist() == orc.refine_alignment(*args[i], 150, 2, om, flag)
+        batch.estimate(True)
+        lls, _ = batch.log_likelihoods()
+        for ll, a in zip(lls, args):
+            ref_col = ll[np.arange(len(ll)), a[1]]
+            assert np.all(ref_col == ref_col[0]) and np.all(np.isfinite(ll))
+            # the true base is the most likely one at (nearly) every position of an error-free synthetic read
+            assert np.mean(np.argmax(ll, axis=1) == a[1]) > 0.97
+        want = np.array(orc.estimate_log_likelihoods(*args[0], 150, 2, om, True))
+        np.testing.assert_allclose(lls[0], want, rtol=1e-9)
+        np.testing.assert_allclose((lls[0] - lls[0][0, args[0][1][0]]) / 10, (want - want[0, args[0][1][0]]) / 10,
+                                   rtol=CHUNK_RTOL, atol=CHUNK_ATOL)
