@@ -89,7 +89,8 @@ struct nvb_batch {
   // workspace
   DevBuf<double> d_pF, d_sF, d_dp;   // DP matrices: mantissa planes
   DevBuf<int32_t> d_pX, d_sX;        // ... and exponent planes
-  DevBuf<int64_t> d_mat_base, d_dp_base;
+  DevBuf<int64_t> d_mat_base, d_dp_base, d_rec_base;
+  DevBuf<uint32_t> d_records;        // path search: one "new row record" bit per cell (path2.cu)
   int64_t ws_limit = 0;
   int64_t launches = 0;
   BatchDev dev{};
@@ -277,58 +278,76 @@ int64_t matrix_cells(const nvb_batch *b, int i, int mode) {
   return b->cells[i];
 }
 
-struct Wave { int b0, b1; };
+struct Wave { int b0, b1; int64_t cells; int maxw; };
+
+// 32-bit words of record bits the path search keeps for read i (path2.cu): rows x chunks x 32
+int64_t record_words(const nvb_batch *b, int i, int mode) {
+  if (b->flags[i]) return 0;
+  const int64_t n = b->ref_off[i + 1] - b->ref_off[i];
+  const int64_t rows = (mode == NVB_MODE_TRANS) ? 2 * n : n + 1;
+  const int chunk = nvbk_path2_chunk_columns();
+  const int64_t nch = (b->maxw[i] + chunk - 1) / chunk;
+  return rows * nch * 32;
+}
 
 // Split the batch into waves of consecutive reads whose two DP matrices (+ path scratch) fit the workspace limit.
 int plan_waves(nvb_batch *b, int mode, bool need_dp, std::vector<Wave> &waves, std::vector<int64_t> &mat_base,
-               std::vector<int64_t> &dp_base, int64_t &max_cells, int64_t &max_dp) {
+               std::vector<int64_t> &dp_base, std::vector<int64_t> &rec_base, int64_t &max_cells, int64_t &max_dp,
+               int64_t &max_rec) {
   int64_t limit = b->ws_limit;
   if (limit <= 0) {
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     // memory already held by this batch's workspace can be reused
-    free_b += (b->d_pF.n + b->d_sF.n + b->d_dp.n) * sizeof(double) + (b->d_pX.n + b->d_sX.n) * sizeof(int32_t);
+    free_b += (b->d_pF.n + b->d_sF.n + b->d_dp.n) * sizeof(double) + (b->d_pX.n + b->d_sX.n + b->d_records.n) * sizeof(int32_t);
     limit = (int64_t)(free_b * 0.7);
   }
   const int n = b->n_reads;
-  mat_base.assign(n, 0); dp_base.assign(n, 0);
+  mat_base.assign(n, 0); dp_base.assign(n, 0); rec_base.assign(n, 0);
   waves.clear();
-  max_cells = 0; max_dp = 0;
+  max_cells = 0; max_dp = 0; max_rec = 0;
   int i = 0;
   while (i < n) {
-    int64_t cells = 0, dp = 0;
+    int64_t cells = 0, dp = 0, rec = 0;
+    int maxw = 0;
     int j = i;
     while (j < n) {
-      int64_t c = matrix_cells(b, j, mode), d = need_dp ? 2 * (int64_t)b->maxw[j] : 0;
-      int64_t bytes = (cells + c) * 2 * (int64_t)(sizeof(double) + sizeof(int32_t)) + (dp + d) * (int64_t)sizeof(double);
+      const int64_t c = matrix_cells(b, j, mode), d = need_dp ? 2 * (int64_t)b->maxw[j] : 0;
+      const int64_t rw = need_dp ? record_words(b, j, mode) : 0;
+      const int64_t bytes = (cells + c) * 2 * (int64_t)(sizeof(double) + sizeof(int32_t)) +
+                            (dp + d) * (int64_t)sizeof(double) + (rec + rw) * (int64_t)sizeof(uint32_t);
       if (bytes > limit && j > i) break;
       if (bytes > limit)
         return fail(NVB_ENOMEM, "read %d needs %lld bytes of DP workspace, limit is %lld", j, (long long)bytes, (long long)limit);
-      mat_base[j] = cells; dp_base[j] = dp;
-      cells += c; dp += d;
+      mat_base[j] = cells; dp_base[j] = dp; rec_base[j] = rec;
+      cells += c; dp += d; rec += rw;
+      if (!b->flags[j]) maxw = std::max(maxw, (int)b->maxw[j]);
       j++;
     }
-    waves.push_back({i, j});
+    waves.push_back({i, j, cells, maxw});
     max_cells = std::max(max_cells, cells);
     max_dp = std::max(max_dp, dp);
+    max_rec = std::max(max_rec, rec);
     i = j;
   }
   return NVB_OK;
 }
 
 int prepare_workspace(nvb_batch *b, int mode, bool need_dp, std::vector<Wave> &waves, cudaStream_t st) {
-  std::vector<int64_t> mat_base, dp_base;
-  int64_t max_cells = 0, max_dp = 0;
-  int rc = plan_waves(b, mode, need_dp, waves, mat_base, dp_base, max_cells, max_dp);
+  std::vector<int64_t> mat_base, dp_base, rec_base;
+  int64_t max_cells = 0, max_dp = 0, max_rec = 0;
+  int rc = plan_waves(b, mode, need_dp, waves, mat_base, dp_base, rec_base, max_cells, max_dp, max_rec);
   if (rc) return rc;
   if (b->d_pF.alloc((size_t)max_cells) != cudaSuccess || b->d_sF.alloc((size_t)max_cells) != cudaSuccess ||
       b->d_pX.alloc((size_t)max_cells) != cudaSuccess || b->d_sX.alloc((size_t)max_cells) != cudaSuccess ||
-      b->d_dp.alloc((size_t)max_dp) != cudaSuccess) {
+      b->d_dp.alloc((size_t)max_dp) != cudaSuccess || b->d_records.alloc((size_t)max_rec) != cudaSuccess) {
     cudaGetLastError();
-    return fail(NVB_ENOMEM, "cannot allocate %lld bytes of DP workspace", (long long)(24 * max_cells + 8 * max_dp));
+    return fail(NVB_ENOMEM, "cannot allocate %lld bytes of DP workspace",
+                (long long)(24 * max_cells + 8 * max_dp + 4 * max_rec));
   }
   CU(upload(b->d_mat_base, mat_base.data(), mat_base.size(), st));
   CU(upload(b->d_dp_base, dp_base.data(), dp_base.size(), st));
+  CU(upload(b->d_rec_base, rec_base.data(), rec_base.size(), st));
   // pageable-host uploads above are complete when cudaMemcpyAsync returns only for small sizes; be explicit:
   CU(cudaStreamSynchronize(st));
   return NVB_OK;
@@ -382,11 +401,14 @@ int nvb_batch_refine(nvb_batch *b, int model_transitions, void *stream) {
                       b->d_sX.p, st))
         return fail(NVB_EINVAL, "min_event_length %d is not supported (maximum 6)", b->dev.mel);
     }
-    if (!getenv("NVB_DEBUG_SKIP_PATH")) {
+    if (!getenv("NVB_DEBUG_SKIP_PATH")) {  // debugging aid: keep the prefix plane for nvb_batch_debug_rows
       StageTimer t(b, 1, st);
-      nvbk_path(b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->d_pF.p, b->d_pX.p, b->d_sF.p, b->d_sX.p, b->d_dp.p,
-                b->d_dp_base.p, b->d_events.p, b->d_status.p, st);
+      nvbk_score(w.cells, b->d_pF.p, b->d_pX.p, b->d_sF.p, b->d_sX.p, st);
+      if (nvbk_path2(b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->d_pF.p, b->d_records.p, b->d_rec_base.p,
+                     b->d_dp.p, b->d_dp_base.p, w.maxw, b->d_events.p, b->d_status.p, st))
+        return fail(NVB_ECUDA, "path kernel: cannot reserve shared memory");
     }
+    b->launches += 1;
     b->launches += 2;
   }
   CU(cudaGetLastError());

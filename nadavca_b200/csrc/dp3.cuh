@@ -1,0 +1,240 @@
+// dp3.cuh -- the scaled linear-domain DP cell shared by the row sweep (rows3.cu) and the SNP kernel (snp3.cu).
+//
+// The reference carries every DP cell as a log-probability and pays one exp + one log per cell
+// (probability.cpp:33-40).  Here a cell is a double mantissa f and an int32 binary exponent e,
+// value = f * 2^e, so a cell update is a couple of FMAs; the only transcendental left is ONE exp per lane and step
+// (the Gaussian emission), computed directly in (mantissa, exponent) form so that no likelihood, however small,
+// ever underflows.  Mathematically this is the same sum-product recurrence as Node::NextRow
+// (node_next_row.h:6-61):
+//     A-row (wobble / transition, m = 0):  A[c] = P[c] + mixemis(c-1) * A[c-1]
+//     B-row (model, m = min_event_length): B[c] = e(c-1) * B[c-1] + (prod_{j=c-m}^{c-1} e(j)) * A[c-m]
+// with P the previous B-row.  One lane owns one (A-row, B-row) pair; lanes form a wavefront skewed by one step,
+// neighbour values travel by warp shuffle.
+//
+// Exponent bookkeeping: every running value (A cell, B cell, each A value in flight to the B-row) carries its OWN
+// exponent.  Multiplying by an emission p * 2^k multiplies the mantissa by p and adds k to the exponent (exact, any
+// range); adding two terms aligns BOTH on the larger exponent (select-free: two power-of-two scale factors, one of
+// them 1.0), so a term is dropped only when it is below 2^-1022 of the other term OF THE SAME CELL -- the reference
+// itself drops it below e^-37 (log(1 + exp(b - a)) == 0).
+//
+// Zero is (0.0, NVB_EZERO) with NVB_EZERO = -2^29.  Exponents of zero mantissas are never special-cased: they drift
+// by the emission exponents like any other (a few thousand per row at most) and stay hundreds of millions below
+// every real exponent (>= -12M for 20k samples at the worst emission), so max() never picks them, and the sum of two
+// of them cannot overflow int32.  Mantissas are renormalised every 8 steps (see NVB_RENORM_MASK).
+//
+// Instruction diet (ncu, profiles/r01b: the v2 kernels were instruction-issue bound at ~190 warp instructions per
+// wavefront step): polynomial coefficients come from the constant bank as DFMA operands instead of 2 UMOV each,
+// the JOIN role shares the B-row code (emission 1, inflow multiplied by the suffix cell), rows without an A-row are
+// handled by data (zero mixture weight, open band) instead of a divergent branch, and the kernel is specialised on the
+// row mode so the plain sweep carries no A-row code and the transition sweep no mixture.
+#pragma once
+#include "common.cuh"
+
+// Mantissas are renormalised when (step & mask) == mask, i.e. every 8 steps.  The period bounds how stale a
+// mantissa can get: alignment takes the larger EXPONENT, so a value whose mantissa has decayed hands its slack to
+// whatever is added to it, and the slack compounds lane after lane (one hop per step).  With at most 2^-1 per step
+// and hop (emission mantissas >= 0.70, transition weight 0.64 * 2^-6) 8 steps x 8 hops stay far inside the double
+// range; 32 steps did not (measured: garbage in the far tails of transition rows).
+#ifndef NVB_RENORM_MASK
+#define NVB_RENORM_MASK 7
+#endif
+
+#define NVB_EZERO (-(1 << 29))  // exponent carried by values that are exactly zero
+
+#define NVB_LN2_HI 6.93147180369123816490e-01
+#define NVB_LN2_LO 1.90821492927058770002e-10
+#define NVB_LOG2E 1.44269504088896338700e+00
+
+// Taylor coefficients 1/13! .. 1/3! of exp(r); read as constant-bank operands of the DFMAs
+static __constant__ double c_exp_poly[11] = {
+    1.6059043836821613e-10, 2.08767569878681e-09,   2.505210838544172e-08,  2.755731922398589e-07,
+    2.7557319223985893e-06, 2.48015873015873e-05,   1.984126984126984e-04,  1.388888888888889e-03,
+    8.333333333333333e-03,  4.1666666666666664e-02, 1.6666666666666666e-01};
+
+// 2^e as a double for e <= 0; e <= -1023 gives +0.0
+__device__ __forceinline__ double pow2neg(int e) {
+  e = max(e, -1023);
+  return __hiloint2double((e + 1023) << 20, 0);
+}
+
+// exp(l) = p * 2^k with p in [0.70, 1.42], any finite l (no underflow: k is returned, not applied).
+// Cody-Waite reduction r = l - k*ln2 (hi/lo) and a degree-13 Taylor polynomial on |r| <= 0.347 (error < 5e-18).
+__device__ __forceinline__ void exp_ext(double l, double &p, int &k) {
+  const double magic = 6755399441055744.0;  // 1.5 * 2^52: rint via add/sub, integer in the low word
+  double t = fma(l, NVB_LOG2E, magic);
+  k = __double2loint(t);
+  double kd = t - magic;
+  double r = fma(-kd, NVB_LN2_HI, l);
+  r = fma(-kd, NVB_LN2_LO, r);
+  double q = c_exp_poly[0];
+#pragma unroll
+  for (int i = 1; i < 11; i++) q = fma(q, r, c_exp_poly[i]);
+  q = fma(q, r, 0.5);
+  q = fma(q, r, 1.0);
+  p = fma(q, r, 1.0);
+}
+
+// natural log of f * 2^E (f > 0), E*ln2 added in two pieces
+__device__ __forceinline__ double log_ext(double f, int E) {
+  if (!(f > 0.0)) return nvb_neg_inf();
+  return fma((double)E, NVB_LN2_HI, log(f)) + (double)E * NVB_LN2_LO;
+}
+
+// value = f * 2^e; zero is (0, NVB_EZERO)
+struct XD {
+  double f;
+  int e;
+};
+
+__device__ __forceinline__ XD xd_make(double f, int e) {
+  XD v;
+  v.f = f; v.e = e;
+  return v;
+}
+__device__ __forceinline__ XD xd_zero() { return xd_make(0.0, NVB_EZERO); }
+
+// a + b, both aligned on the larger exponent (no selects; one of the two scale factors is 1.0)
+__device__ __forceinline__ XD xd_add(XD a, XD b) {
+  XD r;
+  r.e = max(a.e, b.e);
+  r.f = fma(b.f, pow2neg(b.e - r.e), a.f * pow2neg(a.e - r.e));
+  return r;
+}
+
+// mantissa back into [1,2) (normal inputs only); zero gets the zero exponent back
+__device__ __forceinline__ void xd_renorm(XD &v) {
+  if (v.f > 0.0) {
+    const int hi = __double2hiint(v.f);
+    v.e += ((hi >> 20) & 0x7ff) - 1023;
+    v.f = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(v.f));
+  } else {
+    v.e = NVB_EZERO;
+  }
+}
+
+enum { NVB_ROLE_IDLE = 0, NVB_ROLE_LOADER = 1, NVB_ROLE_PAIR = 2, NVB_ROLE_JOIN = 3 };
+
+// Per-lane constants of one stripe / task.
+struct LaneCfg {
+  int role;
+  int ws, we;        // A-row band (INT_MIN..INT_MAX for lanes without an A-row: their A-row is P itself).  Both ends
+                     // are needed: the far end of the band is `we` in a forward sweep and `ws` in a reverse sweep
+  int ms, me;        // B-row band; LOADER: band of the row it loads; JOIN: band of the closing suffix row
+  double mu, ac, mc; // own Gaussian emission (PAIR: model row; LOADER: the row before the first pair; JOIN: last+1)
+  double cm;         // A-row mixture weight: exp(-2) (kmer_model.cpp:60), 0 for lanes without an A-row
+  int abias;         // 0, or NVB_EZERO for lanes without an A-row (their mixture term must stay zero-class)
+  double pc;         // transition rows: constant emission 0.01 = 0.64 * 2^-6, or 0 (kmer_model.cpp:64-94)
+  int kc;            // ... and its exponent (-6 / NVB_EZERO)
+};
+
+__device__ __forceinline__ void lane_cfg_clear(LaneCfg &L) {
+  L.role = NVB_ROLE_IDLE; L.ws = -0x7fffffff - 1; L.we = 0x7fffffff; L.ms = 1; L.me = 0;
+  L.mu = 0; L.ac = 0; L.mc = 0; L.cm = 0; L.abias = NVB_EZERO; L.pc = 0; L.kc = NVB_EZERO;
+}
+
+template <int MEL>
+struct LaneState {
+  XD mod, w;                    // running B-row / A-row cells
+  XD q[MEL > 0 ? MEL : 1];      // A-row outputs in flight to the B-row (delay = min_event_length)
+};
+
+template <int MEL>
+__device__ __forceinline__ void lane_reset(LaneState<MEL> &S) {
+  S.mod = xd_zero(); S.w = xd_zero();
+#pragma unroll
+  for (int i = 0; i < (MEL > 0 ? MEL : 1); i++) S.q[i] = xd_zero();
+}
+
+// Outputs of a lane at one step, consumed by lane+1 at the next step.
+struct LaneOut {
+  double f;  // B-row value at this step's column (masked to the row's band): f * 2^E
+  int E;
+  double p;  // own emission at this step's sample: p * 2^k
+  int k;
+};
+
+// One wavefront step of one lane.  `c` is the column, `x` the sample this step's emissions are evaluated at,
+// `in` the neighbour's output of the previous step.  JOIN lanes (WITH_JOIN kernels only) run the same code with
+// emission 1 on their B-row and their A-row cell multiplied by the closing suffix cell (sF, sX), which makes the B
+// cell the running sum of Node::TotalLikelihood (node.cpp:31-37), delayed by MEL steps; other lanes pass (1.0, 0).
+// `aout` receives the A-row cell (for callers that store it).
+template <int MEL, int MODE, bool WITH_JOIN>
+__device__ __forceinline__ void lane_step(const LaneCfg &L, LaneState<MEL> &S, int c, double x, const LaneOut &in,
+                                          double sF, int sX, LaneOut &out, XD &aout) {
+  // own emission, reference formula ac - d*d*mc (kmer_model.cpp:47-51)
+  const double d = x - L.mu;
+  const double l = L.ac - d * d * L.mc;
+  double p;
+  int kk;
+  exp_ext(l, p, kk);
+  out.p = p;
+  out.k = kk;
+
+  const XD pm = xd_make(in.f, in.E);
+  XD wout;
+  if (MODE == NVB_MODE_PLAIN) {
+    wout = pm;
+  } else {
+    // A[c] = P[c] + mix * A[c-1]
+    XD mix;
+    if (MODE == NVB_MODE_TRANS) {
+      mix = xd_make(L.pc, L.kc);
+    } else {
+      mix = xd_add(xd_make(p, kk), xd_make(in.p, in.k));  // own + neighbour emission, weight exp(-2) each
+      mix.f *= L.cm;
+      mix.e += L.abias;
+    }
+    S.w = xd_add(xd_make(mix.f * S.w.f, S.w.e + mix.e), pm);
+    wout = (c >= L.ws && c <= L.we) ? S.w : xd_zero();
+  }
+  aout = wout;
+
+  double pb = p;
+  int kb = kk;
+  XD push = wout;
+  if (WITH_JOIN) {
+    const bool join = L.role == NVB_ROLE_JOIN;
+    pb = join ? 1.0 : p;
+    kb = join ? 0 : kk;
+    push = xd_make(wout.f * sF, wout.e + sX);
+  }
+  // B[c] = e(c-1) * B[c-1] + (product of the last m emissions) * A[c-m]
+  XD popped;
+  if (MEL == 0) {
+    popped = push;
+  } else {
+#pragma unroll
+    for (int i = 0; i < MEL; i++) { S.q[i].f *= pb; S.q[i].e += kb; }
+    popped = S.q[MEL - 1];
+#pragma unroll
+    for (int i = MEL - 1; i > 0; i--) S.q[i] = S.q[i - 1];
+    S.q[0] = push;
+  }
+  S.mod = xd_add(xd_make(pb * S.mod.f, S.mod.e + kb), popped);
+  const bool inb = (c >= L.ms) && (c <= L.me);
+  out.f = inb ? S.mod.f : 0.0;
+  out.E = inb ? S.mod.e : NVB_EZERO;
+}
+
+// Mantissa renormalisation (call on a warp-uniform schedule, every 32 steps).
+template <int MEL>
+__device__ __forceinline__ void lane_renorm(LaneState<MEL> &S) {
+  xd_renorm(S.mod);
+  xd_renorm(S.w);
+#pragma unroll
+  for (int i = 0; i < (MEL > 0 ? MEL : 1); i++) xd_renorm(S.q[i]);
+}
+
+template <int MODE>
+__device__ __forceinline__ LaneOut shfl_up_out(const LaneOut &o) {
+  LaneOut r;
+  r.f = __shfl_up_sync(NVB_FULL, o.f, 1);
+  r.E = __shfl_up_sync(NVB_FULL, o.E, 1);
+  if (MODE == NVB_MODE_WOBBLE) {  // only the wobble mixture needs the neighbour's emission
+    r.p = __shfl_up_sync(NVB_FULL, o.p, 1);
+    r.k = __shfl_up_sync(NVB_FULL, o.k, 1);
+  } else {
+    r.p = 0.0; r.k = NVB_EZERO;
+  }
+  return r;
+}

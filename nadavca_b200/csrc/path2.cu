@@ -1,0 +1,242 @@
+// path2.cu -- posterior rows, max-product path search and traceback of RefineAlignment, second generation.
+//
+// Replaces reference nadavca/dtw/dtw.cpp:199-227 with Node::operator* (node.cpp:23-29) and
+// PathSearchingNode::NextRow / GetBestIndex / GetPrevious (node.cpp:39-91).
+//
+// Stage 1, score_kernel (fully parallel, HBM-bound): score = log(prefix * suffix) for every stored cell, formed
+//   from the (mantissa, exponent) planes written by rows2.cu and written over the prefix mantissa plane.
+// Stage 2, path2_kernel (one warp per read, rows in order): dp[r][c] = score[r][c] + max_{i' <= c - m} dp[r-1][i'].
+//   The running "best predecessor" of the reference (node.cpp:68-89) is a prefix maximum of the previous dp row; it
+//   is kept in shared memory as M[i] = max(dp[r-1][..i]) so a row is: K consecutive columns per lane, K lookups,
+//   one lane-local scan, one 5-step warp max-scan.  The reference's back-pointer prev[c] is the FIRST index
+//   attaining that maximum (strict '>' while scanning upwards, node.cpp:72-75,82-85), i.e. the last column i' <= c-m
+//   at which dp[r-1] set a new strict record.  So one bit per cell ("this cell is a new record of its row") replaces
+//   the 4-byte back-pointer, and the traceback (dtw.cpp:215-227) is a find-last-set over the record bits of the
+//   row above, done by the whole warp with one ballot per row.
+#include <stdio.h>
+#include "dp3.cuh"
+#include "kernels.h"
+
+namespace {
+
+constexpr int PK = 11;               // columns per lane and chunk; odd => conflict-free shared-memory strides
+constexpr int PCHUNK = PK * NVB_WARP;  // 352 columns per chunk
+
+__global__ void __launch_bounds__(256) score_kernel(int64_t total, double *pF, const int32_t *pX, const double *sF,
+                                                    const int32_t *sX) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < total; x += stride)
+    pF[x] = log_ext(pF[x] * __ldg(sF + x), __ldg(pX + x) + __ldg(sX + x));
+}
+
+__device__ __forceinline__ void row_geom2(const ReadView &v, int mode, int r, int &s, int &e, int64_t &off) {
+  int j;
+  if (mode == NVB_MODE_TRANS) { j = (r + 1) >> 1; off = trans_row_off(v, r); }
+  else { j = r; off = v.coff[r]; }
+  s = v.bs[j];
+  e = v.be[j];
+}
+
+__device__ __forceinline__ double warp_excl_max(double x, int lane) {
+#pragma unroll
+  for (int o = 1; o < NVB_WARP; o <<= 1) {
+    const double y = __shfl_up_sync(NVB_FULL, x, o);
+    if (lane >= o) x = fmax(x, y);
+  }
+  const double y = __shfl_up_sync(NVB_FULL, x, 1);
+  return lane ? y : nvb_neg_inf();
+}
+
+// Last record bit at relative index <= t of a row whose record words start at `fl` (nch chunks of 32 words).
+// `w0` is the already loaded word of this lane for chunk t / PCHUNK when have_w0.  Returns -1 when there is none.
+__device__ __forceinline__ int find_last_record(const uint32_t *fl, int t, int lane, bool have_w0, uint32_t w0) {
+  if (t < 0) return -1;
+  int ch = t / PCHUNK;
+  int tl = t - ch * PCHUNK;
+  for (;;) {
+    uint32_t w = have_w0 ? w0 : __ldcg(fl + ch * NVB_WARP + lane);
+    have_w0 = false;
+    const int lane_t = tl / PK, bit_t = tl - lane_t * PK;
+    if (lane > lane_t) w = 0;
+    else if (lane == lane_t) w &= (2u << bit_t) - 1u;
+    const unsigned any = __ballot_sync(NVB_FULL, w != 0);
+    if (any) {
+      const int hl = 31 - __clz(any);
+      const uint32_t wv = __shfl_sync(NVB_FULL, w, hl);
+      return ch * PCHUNK + hl * PK + (31 - __clz(wv));
+    }
+    if (--ch < 0) return -1;
+    tl = PCHUNK - 1;
+  }
+}
+
+__global__ void __launch_bounds__(128) path2_kernel(BatchDev B, int mode, int b0, int n_items, const int64_t *mat_base,
+                                                    const double *score, uint32_t *records, const int64_t *rec_base,
+                                                    double *gscratch, const int64_t *dp_base, int smem_width,
+                                                    int32_t *events, int32_t *status) {
+  extern __shared__ double smem[];
+  const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * (blockDim.x >> 5) + wic;
+  if (item >= n_items) return;
+  const int b = b0 + item;
+  ReadView v = read_view(B, b);
+  const int n = v.n;
+  int32_t *ev = events + 2 * B.ref_off[b];
+  if (B.flags[b]) {
+    for (int i = lane; i < 2 * n; i += NVB_WARP) ev[i] = -1;
+    if (lane == 0) status[b] = B.flags[b];
+    return;
+  }
+  const double NINF = nvb_neg_inf();
+  const int R = (mode == NVB_MODE_TRANS) ? 2 * n : n + 1;
+  const int maxw = B.max_width[b];
+  const int nch = (maxw + PCHUNK - 1) / PCHUNK;
+  const double *SC = score + mat_base[b];
+  uint32_t *FL = records + rec_base[b];
+  double *Mprev, *Mcur;
+  if (smem_width > 0) { Mprev = smem + (size_t)wic * 2 * smem_width; Mcur = Mprev + smem_width; }
+  else { Mprev = gscratch + dp_base[b]; Mcur = Mprev + maxw; }
+
+  int s, e, ps = 0, pe = -1;
+  int64_t off;
+  row_geom2(v, mode, 0, s, e, off);
+  double cur[PK], nxt[PK];
+  {
+    const int c0 = s + lane * PK;
+#pragma unroll
+    for (int j = 0; j < PK; j++) cur[j] = (c0 + j <= e) ? __ldg(SC + off + (c0 + j - s)) : NINF;
+  }
+  for (int r = 0; r < R; r++) {
+    const int m = (r == 0) ? 0 : ((mode == NVB_MODE_TRANS && ((r - 1) & 1)) ? 0 : B.mel);  // dtw.cpp:165-179
+    // prefetch the first chunk of the next row while this one is processed
+    int ns = 0, ne = -1;
+    int64_t noff = 0;
+    if (r + 1 < R) {
+      row_geom2(v, mode, r + 1, ns, ne, noff);
+      const int c0 = ns + lane * PK;
+#pragma unroll
+      for (int j = 0; j < PK; j++) nxt[j] = (c0 + j <= ne) ? __ldg(SC + noff + (c0 + j - ns)) : NINF;
+    }
+    const int w = e - s + 1;
+    double chunk_carry = NINF;
+    for (int ch = 0; ch * PCHUNK < w; ch++) {
+      const int c0 = s + ch * PCHUNK + lane * PK;
+      double dp[PK];
+#pragma unroll
+      for (int j = 0; j < PK; j++) {
+        const int c = c0 + j;
+        double sc = (ch == 0) ? cur[j] : ((c <= e) ? __ldg(SC + off + (c - s)) : NINF);
+        if (r > 0) {
+          // best predecessor over i' <= c - m inside the previous row's band (node.cpp:68-89)
+          const int q = c - m;
+          const double bv = (c <= e && q >= ps) ? Mprev[min(q, pe) - ps] : NINF;
+          sc = bv + sc;
+        }
+        dp[j] = (c <= e) ? sc : NINF;
+      }
+      // lane-local inclusive prefix maxima, then the warp-wide exclusive carry
+      double lm[PK];
+      lm[0] = dp[0];
+#pragma unroll
+      for (int j = 1; j < PK; j++) lm[j] = fmax(lm[j - 1], dp[j]);
+      const double carry = fmax(chunk_carry, warp_excl_max(lm[PK - 1], lane));
+      uint32_t bits = 0;
+      double before = carry;
+#pragma unroll
+      for (int j = 0; j < PK; j++) {
+        if (dp[j] > before) bits |= 1u << j;  // strict '>': the lowest index wins ties (node.cpp:72-75)
+        before = fmax(before, dp[j]);
+        if (c0 + j <= e) Mcur[c0 + j - s] = before;
+      }
+      FL[((int64_t)r * nch + ch) * NVB_WARP + lane] = bits;
+      chunk_carry = __shfl_sync(NVB_FULL, before, NVB_WARP - 1);
+    }
+    __syncwarp();
+#ifdef NVB_TRACE
+    if (lane == 0 && b == b0) printf("row %d band %d..%d off %lld m %d carry %g cur0 %g\n", r, s, e, (long long)off, m, chunk_carry, cur[0]);
+#endif
+    double *t = Mprev; Mprev = Mcur; Mcur = t;
+    ps = s; pe = e;
+    s = ns; e = ne; off = noff;
+#pragma unroll
+    for (int j = 0; j < PK; j++) cur[j] = nxt[j];
+  }
+  __threadfence_block();
+  __syncwarp();
+
+  // GetBestIndex on the last row (node.cpp:48-58): first index of the row maximum = its last record
+  int rs, re;
+  row_geom2(v, mode, R - 1, rs, re, off);
+  int rel = find_last_record(FL + (int64_t)(R - 1) * nch * NVB_WARP, re - rs, lane, false, 0);
+  if (rel < 0) {  // no valid path in the band (dtw.cpp:211-213)
+    for (int i = lane; i < 2 * n; i += NVB_WARP) ev[i] = -1;
+    if (lane == 0) status[b] = 1;
+    return;
+  }
+  // traceback (dtw.cpp:215-227); the record words of the next 8 rows above are fetched together
+  constexpr int G = 8;
+  for (int rt = R - 1; rt >= 0; rt -= G) {
+    uint32_t pre[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      const int rr = rt - g - 1;
+      pre[g] = (nch == 1 && rr >= 0) ? __ldcg(FL + (int64_t)rr * NVB_WARP + lane) : 0u;
+    }
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      const int r = rt - g;
+      if (r < 0) break;
+      row_geom2(v, mode, r, rs, re, off);
+      const int col = rs + rel;
+      if (lane == 0) {
+        if (mode == NVB_MODE_TRANS) {
+          ev[r] = col;  // events[r/2][r%2]
+        } else {
+          if (r > 0) ev[2 * (r - 1) + 1] = col;
+          if (r + 1 < R) ev[2 * r] = col;
+        }
+      }
+      if (r > 0) {
+        const int m = (mode == NVB_MODE_TRANS && ((r - 1) & 1)) ? 0 : B.mel;
+        int qs, qe;
+        int64_t qoff;
+        row_geom2(v, mode, r - 1, qs, qe, qoff);
+        const int q = min(col - m, qe) - qs;
+        rel = find_last_record(FL + (int64_t)(r - 1) * nch * NVB_WARP, q, lane, nch == 1, pre[g]);
+      }
+    }
+  }
+  if (lane == 0) status[b] = 0;
+}
+
+}  // namespace
+
+int nvbk_path2_chunk_columns() { return PCHUNK; }
+
+void nvbk_score(int64_t total_cells, double *pF, const int32_t *pX, const double *sF, const int32_t *sX,
+                cudaStream_t st) {
+  if (total_cells <= 0) return;
+  const int64_t want = (total_cells + 255) / 256;
+  const unsigned blocks = (unsigned)(want < 148 * 32 ? want : 148 * 32);
+  score_kernel<<<blocks, 256, 0, st>>>(total_cells, pF, pX, sF, sX);
+}
+
+int nvbk_path2(const BatchDev &B, int mode, int b0, int b1, const int64_t *d_mat_base, const double *score,
+               uint32_t *d_records, const int64_t *d_rec_base, double *d_dp, const int64_t *d_dp_base, int wave_maxw,
+               int32_t *d_events, int32_t *d_status, cudaStream_t st) {
+  const int n_items = b1 - b0;
+  if (n_items <= 0) return 0;
+  // shared memory: two prefix-maximum rows per warp; fall back to the global scratch rows for very wide bands
+  const size_t per_warp = (size_t)2 * wave_maxw * sizeof(double);
+  int warps = 4, smem_width = wave_maxw;
+  while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
+  if (per_warp * warps > 200 * 1024) smem_width = 0;
+  const size_t smem = smem_width ? per_warp * warps : 0;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(path2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -1;
+  }
+  path2_kernel<<<(n_items + warps - 1) / warps, warps * NVB_WARP, smem, st>>>(
+      B, mode, b0, n_items, d_mat_base, score, d_records, d_rec_base, d_dp, d_dp_base, smem_width, d_events, d_status);
+  return 0;
+}

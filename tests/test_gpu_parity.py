@@ -212,7 +212,7 @@ def test_workspace_waves_give_identical_results(default_model):
     gm = dtw.KmerModel(k, cp, 4, mean, sigma)
     lists = [[c[i] for c in cases] for i in (2, 3, 4, 5, 6)]
     out = []
-    for limit in (0, 60_000):
+    for limit in (0, 90_000):
         with dtw.Batch(gm, *lists, bw, mel, workspace_limit=limit) as batch:
             batch.refine(True)
             ev, _ = batch.events()
