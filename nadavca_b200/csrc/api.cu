@@ -397,9 +397,10 @@ int nvb_batch_refine(nvb_batch *b, int model_transitions, void *stream) {
   for (const Wave &w : waves) {
     {
       StageTimer t(b, 0, st);
-      if (nvbk_sweep2(b->model->dev, b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->d_pF.p, b->d_pX.p, b->d_sF.p,
-                      b->d_sX.p, st))
-        return fail(NVB_EINVAL, "min_event_length %d is not supported (maximum 6)", b->dev.mel);
+      const int src = nvbk_sweep2(b->model->dev, b->dev, mode, w.b0, w.b1, w.maxw, b->d_mat_base.p, b->d_pF.p,
+                                  b->d_pX.p, b->d_sF.p, b->d_sX.p, st);
+      if (src == -1) return fail(NVB_EINVAL, "min_event_length %d is not supported (maximum 6)", b->dev.mel);
+      if (src) return fail(NVB_ENOMEM, "band row of %d columns does not fit the sweep's shared-memory hand-off rows", w.maxw);
     }
     if (!getenv("NVB_DEBUG_SKIP_PATH")) {  // debugging aid: keep the prefix plane for nvb_batch_debug_rows
       StageTimer t(b, 1, st);
@@ -432,8 +433,10 @@ int nvb_batch_estimate(nvb_batch *b, int model_wobbling, void *stream) {
   for (const Wave &w : waves) {
     {
       StageTimer t(b, 0, st);
-      if (nvbk_sweep2(M, b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->d_pF.p, b->d_pX.p, b->d_sF.p, b->d_sX.p, st))
-        return fail(NVB_EINVAL, "min_event_length %d is not supported (maximum 6)", b->dev.mel);
+      const int src = nvbk_sweep2(M, b->dev, mode, w.b0, w.b1, w.maxw, b->d_mat_base.p, b->d_pF.p, b->d_pX.p,
+                                  b->d_sF.p, b->d_sX.p, st);
+      if (src == -1) return fail(NVB_EINVAL, "min_event_length %d is not supported (maximum 6)", b->dev.mel);
+      if (src) return fail(NVB_ENOMEM, "band row of %d columns does not fit the sweep's shared-memory hand-off rows", w.maxw);
     }
     {
       StageTimer t(b, 2, st);

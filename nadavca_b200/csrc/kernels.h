@@ -6,10 +6,11 @@
 void nvbk_band(const BatchDev &B, int64_t *d_summary, cudaStream_t st);
 void nvbk_expected_signal(const ModelDev &M, const BatchDev &B, int64_t total, double *d_out, cudaStream_t st);
 
-// rows2.cu: forward + backward banded rows for reads [b0,b1) (one warp per read and direction); rows are stored
-// as a mantissa plane (double) and an exponent plane (int32).  Returns -1 for an unsupported min_event_length.
-int nvbk_sweep2(const ModelDev &M, const BatchDev &B, int mode, int b0, int b1, const int64_t *d_mat_base,
-                double *pF, int32_t *pX, double *sF, int32_t *sX, cudaStream_t st);
+// rows4.cu: forward + backward banded rows for reads [b0,b1): one CTA per (read, direction), stripes pipelined over
+// its warps; rows are stored as a mantissa plane (double) and an exponent plane (int32).  wave_maxw = widest band
+// row of the wave.  Returns -1 for an unsupported min_event_length, -2 when the hand-off rows do not fit shared memory.
+int nvbk_sweep2(const ModelDev &M, const BatchDev &B, int mode, int b0, int b1, int wave_maxw,
+                const int64_t *d_mat_base, double *pF, int32_t *pX, double *sF, int32_t *sX, cudaStream_t st);
 // no-SNP total (dtw.cpp:83-85) written into the reference-base column of out_ll
 void nvbk_no_snp2(const ModelDev &M, const BatchDev &B, int b0, int b1, const int64_t *d_mat_base, const double *pF,
                   const int32_t *pX, const double *sF, const int32_t *sX, double *d_out_ll, cudaStream_t st);
