@@ -42,6 +42,9 @@ int nvb_abi_version(void);
 const char *nvb_last_error(void);
 /* number of usable CUDA devices (0 when there is no driver/GPU); never fails */
 int nvb_device_count(void);
+/* Device buffers of destroyed batches / models are kept in a per-device cache for re-use (cudaFree costs far more
+ * than a batch's kernels); this hands the cached blocks back to the driver. */
+int nvb_trim_memory(int device);
 
 /* ---- k-mer model: replaces class KmerModel (dtwmodule.cpp:12-18, kmer_model.cpp:6-42) -------------------- */
 /* mean/sigma have alphabet_size^k entries; tables (mean, log(1/sqrt(2 pi s^2)), 1/(2 s^2)) are built on the host
@@ -100,7 +103,9 @@ int nvb_batch_set_signal(nvb_batch *batch, const double *signal);
 /* limit for the DP matrices kept in HBM at one time (bytes; 0 = 70% of the free device memory).  Batches that
  * need more are processed in several waves of reads. */
 int nvb_batch_set_workspace_limit(nvb_batch *batch, int64_t bytes);
-/* run the kernels on `stream`; asynchronous with respect to the host except for wave planning */
+/* run the kernels on `stream`; asynchronous with respect to the host except for wave planning.  The DP matrices live
+ * in a workspace owned by the MODEL and shared by its batches (it grows to the largest wave seen and is freed with the
+ * model): runs on batches of one model must not overlap in time -- issue them on one stream. */
 int nvb_batch_refine(nvb_batch *batch, int model_transitions, void *stream);
 int nvb_batch_estimate(nvb_batch *batch, int model_wobbling, void *stream);
 /* results of the last run (blocking copies) */

@@ -7,6 +7,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -34,20 +36,74 @@ int fail(int code, const char *fmt, ...) {
       return fail(NVB_ECUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, __LINE__, #expr); \
   } while (0)
 
+// Device memory comes from a per-device cache of freed blocks: cudaFree of the ~20 buffers of a batch costs hundreds
+// of milliseconds on this driver (measured: 280-650 ms per nvb_batch_destroy of a 1000-read batch), far more than the
+// kernels of the batch.  Blocks are handed back to the driver only by nvb_trim_memory() or when an allocation fails.
+struct DevicePool {
+  std::mutex m;
+  std::multimap<size_t, void *> free_blocks;
+  size_t cached = 0;
+};
+DevicePool g_pool[64];
+
+void pool_trim(int device) {
+  DevicePool &P = g_pool[device & 63];
+  std::lock_guard<std::mutex> lock(P.m);
+  for (auto &kv : P.free_blocks) cudaFree(kv.second);
+  P.free_blocks.clear();
+  P.cached = 0;
+}
+
+cudaError_t pool_alloc(void **out, size_t bytes, size_t *capacity, int *device) {
+  bytes = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  *device = dev;
+  DevicePool &P = g_pool[dev & 63];
+  {
+    std::lock_guard<std::mutex> lock(P.m);
+    auto it = P.free_blocks.lower_bound(bytes);
+    if (it != P.free_blocks.end() && it->first <= bytes + bytes / 4 + (1 << 20)) {
+      *out = it->second; *capacity = it->first;
+      P.cached -= it->first;
+      P.free_blocks.erase(it);
+      return cudaSuccess;
+    }
+  }
+  e = cudaMalloc(out, bytes);
+  if (e != cudaSuccess) {  // give the cached blocks back and retry once
+    cudaGetLastError();
+    pool_trim(dev);
+    e = cudaMalloc(out, bytes);
+  }
+  *capacity = bytes;
+  return e;
+}
+
+void pool_free(void *p, size_t capacity, int device) {
+  DevicePool &P = g_pool[device & 63];
+  std::lock_guard<std::mutex> lock(P.m);
+  P.free_blocks.emplace(capacity, p);
+  P.cached += capacity;
+}
+
 template <class T>
 struct DevBuf {
   T *p = nullptr;
-  size_t n = 0;
+  size_t n = 0;         // elements requested
+  size_t capacity = 0;  // bytes of the block
+  int device = 0;
   cudaError_t alloc(size_t count) {
-    if (count <= n && p) return cudaSuccess;
+    if (p && count * sizeof(T) <= capacity) { n = std::max(n, count); return cudaSuccess; }
     release();
-    cudaError_t e = cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T));
-    if (e == cudaSuccess) n = count; else p = nullptr;
+    cudaError_t e = pool_alloc((void **)&p, count * sizeof(T), &capacity, &device);
+    if (e == cudaSuccess) n = count; else { p = nullptr; capacity = 0; }
     return e;
   }
   void release() {
-    if (p) cudaFree(p);
-    p = nullptr; n = 0;
+    if (p) pool_free(p, capacity, device);
+    p = nullptr; n = 0; capacity = 0;
   }
   ~DevBuf() { release(); }
 };
@@ -62,11 +118,25 @@ cudaError_t upload(DevBuf<T> &buf, const T *src, size_t count, cudaStream_t st) 
 
 }  // namespace
 
+// DP workspace: owned by the model and shared by all of its batches (allocating and freeing several GB per batch
+// costs tens of milliseconds per call); it only ever grows and is released with the model.
+struct Workspace {
+  DevBuf<double> pF, sF, dp;   // DP matrices: mantissa planes; path-search scratch rows
+  DevBuf<int32_t> pX, sX;      // ... and exponent planes
+  DevBuf<uint32_t> records;    // path search: one "new row record" bit per cell (path2.cu)
+  size_t bytes() const {
+    return pF.capacity + sF.capacity + dp.capacity + pX.capacity + sX.capacity + records.capacity;
+  }
+};
+
 struct nvb_model {
   int device = 0;
   ModelDev dev{};
   DevBuf<double> mean, ac, mc;
+  Workspace ws;
 };
+
+struct Wave { int b0, b1; int64_t cells; int maxw; };
 
 struct nvb_batch {
   nvb_model *model = nullptr;
@@ -86,13 +156,16 @@ struct nvb_batch {
   DevBuf<int32_t> d_events, d_status;
   DevBuf<double> d_ll;
   bool have_events = false, have_ll = false;
-  // workspace
-  DevBuf<double> d_pF, d_sF, d_dp;   // DP matrices: mantissa planes
-  DevBuf<int32_t> d_pX, d_sX;        // ... and exponent planes
+  // per-read offsets into the model's DP workspace, valid for the last run
   DevBuf<int64_t> d_mat_base, d_dp_base, d_rec_base;
-  DevBuf<uint32_t> d_records;        // path search: one "new row record" bit per cell (path2.cu)
   int64_t ws_limit = 0;
   int64_t launches = 0;
+  // plan of the last run (see prepare_workspace)
+  int plan_mode = -1;
+  bool plan_dp = false;
+  int64_t plan_limit = -1;
+  int64_t plan_max[3] = {0, 0, 0};
+  std::vector<Wave> plan_waves_cache;
   BatchDev dev{};
   // optional per-stage timing
   bool timing = false;
@@ -167,6 +240,7 @@ nvb_model *nvb_model_create(int k, int central_position, int alphabet_size, cons
 void nvb_model_destroy(nvb_model *model) {
   if (!model) return;
   cudaSetDevice(model->device);
+  cudaDeviceSynchronize();
   delete model;
 }
 
@@ -278,7 +352,6 @@ int64_t matrix_cells(const nvb_batch *b, int i, int mode) {
   return b->cells[i];
 }
 
-struct Wave { int b0, b1; int64_t cells; int maxw; };
 
 // 32-bit words of record bits the path search keeps for read i (path2.cu): rows x chunks x 32
 int64_t record_words(const nvb_batch *b, int i, int mode) {
@@ -299,7 +372,7 @@ int plan_waves(nvb_batch *b, int mode, bool need_dp, std::vector<Wave> &waves, s
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     // memory already held by this batch's workspace can be reused
-    free_b += (b->d_pF.n + b->d_sF.n + b->d_dp.n) * sizeof(double) + (b->d_pX.n + b->d_sX.n + b->d_records.n) * sizeof(int32_t);
+    free_b += b->model->ws.bytes();
     limit = (int64_t)(free_b * 0.7);
   }
   const int n = b->n_reads;
@@ -336,20 +409,32 @@ int plan_waves(nvb_batch *b, int mode, bool need_dp, std::vector<Wave> &waves, s
 int prepare_workspace(nvb_batch *b, int mode, bool need_dp, std::vector<Wave> &waves, cudaStream_t st) {
   std::vector<int64_t> mat_base, dp_base, rec_base;
   int64_t max_cells = 0, max_dp = 0, max_rec = 0;
-  int rc = plan_waves(b, mode, need_dp, waves, mat_base, dp_base, rec_base, max_cells, max_dp, max_rec);
-  if (rc) return rc;
-  if (b->d_pF.alloc((size_t)max_cells) != cudaSuccess || b->d_sF.alloc((size_t)max_cells) != cudaSuccess ||
-      b->d_pX.alloc((size_t)max_cells) != cudaSuccess || b->d_sX.alloc((size_t)max_cells) != cudaSuccess ||
-      b->d_dp.alloc((size_t)max_dp) != cudaSuccess || b->d_records.alloc((size_t)max_rec) != cudaSuccess) {
+  // The plan of the previous run is kept: repeating a run needs no host planning, no uploads and no synchronisation,
+  // so consecutive runs queue back to back on the stream.
+  const bool cached = b->plan_mode == mode && b->plan_dp == need_dp && b->plan_limit == b->ws_limit;
+  if (cached) {
+    waves = b->plan_waves_cache;
+    max_cells = b->plan_max[0]; max_dp = b->plan_max[1]; max_rec = b->plan_max[2];
+  } else {
+    int rc = plan_waves(b, mode, need_dp, waves, mat_base, dp_base, rec_base, max_cells, max_dp, max_rec);
+    if (rc) return rc;
+  }
+  if (b->model->ws.pF.alloc((size_t)max_cells) != cudaSuccess || b->model->ws.sF.alloc((size_t)max_cells) != cudaSuccess ||
+      b->model->ws.pX.alloc((size_t)max_cells) != cudaSuccess || b->model->ws.sX.alloc((size_t)max_cells) != cudaSuccess ||
+      b->model->ws.dp.alloc((size_t)max_dp) != cudaSuccess || b->model->ws.records.alloc((size_t)max_rec) != cudaSuccess) {
     cudaGetLastError();
     return fail(NVB_ENOMEM, "cannot allocate %lld bytes of DP workspace",
                 (long long)(24 * max_cells + 8 * max_dp + 4 * max_rec));
   }
+  if (cached) return NVB_OK;
   CU(upload(b->d_mat_base, mat_base.data(), mat_base.size(), st));
   CU(upload(b->d_dp_base, dp_base.data(), dp_base.size(), st));
   CU(upload(b->d_rec_base, rec_base.data(), rec_base.size(), st));
   // pageable-host uploads above are complete when cudaMemcpyAsync returns only for small sizes; be explicit:
   CU(cudaStreamSynchronize(st));
+  b->plan_mode = mode; b->plan_dp = need_dp; b->plan_limit = b->ws_limit;
+  b->plan_waves_cache = waves;
+  b->plan_max[0] = max_cells; b->plan_max[1] = max_dp; b->plan_max[2] = max_rec;
   return NVB_OK;
 }
 
@@ -369,7 +454,16 @@ nvb_batch *nvb_batch_create(nvb_model *model, const nvb_reads *reads) {
 void nvb_batch_destroy(nvb_batch *batch) {
   if (!batch) return;
   cudaSetDevice(batch->model->device);
+  cudaDeviceSynchronize();  // its blocks go back to the cache: nothing may still be using them
   delete batch;
+}
+
+int nvb_trim_memory(int device) {
+  if (nvb_device_count() <= device || device < 0) return fail(NVB_ECUDA, "CUDA device %d not available", device);
+  CU(cudaSetDevice(device));
+  CU(cudaDeviceSynchronize());
+  pool_trim(device);
+  return NVB_OK;
 }
 
 int nvb_batch_set_signal(nvb_batch *b, const double *signal) {
@@ -397,16 +491,16 @@ int nvb_batch_refine(nvb_batch *b, int model_transitions, void *stream) {
   for (const Wave &w : waves) {
     {
       StageTimer t(b, 0, st);
-      const int src = nvbk_sweep2(b->model->dev, b->dev, mode, w.b0, w.b1, w.maxw, b->d_mat_base.p, b->d_pF.p,
-                                  b->d_pX.p, b->d_sF.p, b->d_sX.p, st);
+      const int src = nvbk_sweep2(b->model->dev, b->dev, mode, w.b0, w.b1, w.maxw, b->d_mat_base.p, b->model->ws.pF.p,
+                                  b->model->ws.pX.p, b->model->ws.sF.p, b->model->ws.sX.p, st);
       if (src == -1) return fail(NVB_EINVAL, "min_event_length %d is not supported (maximum 6)", b->dev.mel);
       if (src) return fail(NVB_ENOMEM, "band row of %d columns does not fit the sweep's shared-memory hand-off rows", w.maxw);
     }
     if (!getenv("NVB_DEBUG_SKIP_PATH")) {  // debugging aid: keep the prefix plane for nvb_batch_debug_rows
       StageTimer t(b, 1, st);
-      nvbk_score(w.cells, b->d_pF.p, b->d_pX.p, b->d_sF.p, b->d_sX.p, st);
-      if (nvbk_path2(b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->d_pF.p, b->d_records.p, b->d_rec_base.p,
-                     b->d_dp.p, b->d_dp_base.p, w.maxw, b->d_events.p, b->d_status.p, st))
+      nvbk_score(w.cells, b->model->ws.pF.p, b->model->ws.pX.p, b->model->ws.sF.p, b->model->ws.sX.p, st);
+      if (nvbk_path2(b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->model->ws.pF.p, b->model->ws.records.p, b->d_rec_base.p,
+                     b->model->ws.dp.p, b->d_dp_base.p, w.maxw, b->d_events.p, b->d_status.p, st))
         return fail(NVB_ECUDA, "path kernel: cannot reserve shared memory");
     }
     b->launches += 1;
@@ -433,21 +527,21 @@ int nvb_batch_estimate(nvb_batch *b, int model_wobbling, void *stream) {
   for (const Wave &w : waves) {
     {
       StageTimer t(b, 0, st);
-      const int src = nvbk_sweep2(M, b->dev, mode, w.b0, w.b1, w.maxw, b->d_mat_base.p, b->d_pF.p, b->d_pX.p,
-                                  b->d_sF.p, b->d_sX.p, st);
+      const int src = nvbk_sweep2(M, b->dev, mode, w.b0, w.b1, w.maxw, b->d_mat_base.p, b->model->ws.pF.p, b->model->ws.pX.p,
+                                  b->model->ws.sF.p, b->model->ws.sX.p, st);
       if (src == -1) return fail(NVB_EINVAL, "min_event_length %d is not supported (maximum 6)", b->dev.mel);
       if (src) return fail(NVB_ENOMEM, "band row of %d columns does not fit the sweep's shared-memory hand-off rows", w.maxw);
     }
     {
       StageTimer t(b, 2, st);
-      nvbk_no_snp2(M, b->dev, w.b0, w.b1, b->d_mat_base.p, b->d_pF.p, b->d_pX.p, b->d_sF.p, b->d_sX.p, b->d_ll.p,
+      nvbk_no_snp2(M, b->dev, w.b0, w.b1, b->d_mat_base.p, b->model->ws.pF.p, b->model->ws.pX.p, b->model->ws.sF.p, b->model->ws.sX.p, b->d_ll.p,
                    st);
     }
     int snp_rc;
     {
       StageTimer t(b, 3, st);
       snp_rc = nvbk_snp2(M, b->dev, model_wobbling, w.b0, w.b1, b->ref_off[w.b0], b->ref_off[w.b1],
-                         b->d_mat_base.p, b->d_pF.p, b->d_pX.p, b->d_sF.p, b->d_sX.p, b->d_ll.p, st);
+                         b->d_mat_base.p, b->model->ws.pF.p, b->model->ws.pX.p, b->model->ws.sF.p, b->model->ws.sX.p, b->d_ll.p, st);
     }
     if (snp_rc) return fail(NVB_EINVAL, "SNP kernel configuration not supported");
     b->launches += 3;
@@ -538,8 +632,8 @@ int nvb_batch_debug_rows(nvb_batch *b, int read, int plane, double *out_log, int
   CU(cudaMemcpy(&base, b->d_mat_base.p + read, sizeof(int64_t), cudaMemcpyDeviceToHost));
   std::vector<double> f((size_t)n_cells);
   std::vector<int32_t> x((size_t)n_cells);
-  CU(cudaMemcpy(f.data(), (plane ? b->d_sF.p : b->d_pF.p) + base, (size_t)n_cells * sizeof(double), cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(x.data(), (plane ? b->d_sX.p : b->d_pX.p) + base, (size_t)n_cells * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(f.data(), (plane ? b->model->ws.sF.p : b->model->ws.pF.p) + base, (size_t)n_cells * sizeof(double), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(x.data(), (plane ? b->model->ws.sX.p : b->model->ws.pX.p) + base, (size_t)n_cells * sizeof(int32_t), cudaMemcpyDeviceToHost));
   for (int64_t i = 0; i < n_cells; i++)
     out_log[i] = f[i] > 0.0 ? log(f[i]) + x[i] * 0.6931471805599453 : -INFINITY;
   return NVB_OK;
