@@ -115,13 +115,15 @@ def band_stats(bands, k, cp, wobbling=True):
         wob_rows = csum[last + 1] - csum[np.maximum(first, 1)] if wobbling else 0  # sum_{j=max(first,1)..last} W[j]
         trail = np.where(last + 1 < n, w[last], 0) if wobbling else 0
         cells['estimate_snp'] += int(3 * (model_rows + wob_rows + trail).sum())
-        # algorithmic traffic: every stored cell written once (8 B) ...
-        bytes_['rows_refine'] += 2 * tot * 8
-        bytes_['rows_estimate'] += 2 * tot * 8
-        # ... the path stage reads prefix + suffix once and writes one back-pointer per cell
-        bytes_['path'] += tot * (16 + 4)
-        # ... every SNP task reads its start prefix row and its closing suffix row, writes one double
-        bytes_['snp'] += int(3 * ((w[first] + w[last + 1]) * 8 + 8).sum())
+        # algorithmic traffic: a stored cell is 12 B (f64 mantissa + i32 exponent);
+        # sweeps write prefix and suffix once ...
+        bytes_['rows_refine'] += 2 * tot * 12
+        bytes_['rows_estimate'] += 2 * tot * 12
+        # ... the score kernel reads both (24 B) and writes the score (8 B), the path kernel reads the score (8 B) and
+        # writes one record bit per cell
+        bytes_['path'] += tot * (24 + 8 + 8) + tot // 8
+        # ... every SNP task streams its start prefix row and its closing suffix row and writes one double
+        bytes_['snp'] += int(3 * ((w[first] + w[last + 1]) * 12 + 8).sum())
     return cells, bytes_
 
 
@@ -461,11 +463,11 @@ def run_ours(args):
                     'd2h_bytes_per_step': d2h, 'steps': e2e_steps},
             'gpu_launches': int(launches_all),
             'clocks': clocks.summary(),
-            'roofline': {'bound': 'hbm', 'kernel': 'snp_kernel', 'achieved': achieved, 'peak': hbm_peak,
-                         'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+            'roofline': {'bound': 'hbm', 'kernel': 'snp3_kernel', 'achieved': achieved, 'peak': hbm_peak,
+                         'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': ncu_traffic(args.reads), 'peak_source': peak_src,
                          'launch_ms': snp_launch_ms, 'algorithmic_bytes_per_launch': snp_bytes_per_launch,
-                         'note': 'the SNP kernel is FP64-issue bound, not HBM bound: see alu'},
-            'alu': {'kernel': 'snp_kernel', 'dp_cells_per_sec': snp_cells_per_s,
+                         'note': 'the SNP kernel is instruction-issue / FP64-pipe bound, not HBM bound: see alu'},
+            'alu': {'kernel': 'snp3_kernel', 'dp_cells_per_sec': snp_cells_per_s,
                     'fp64_fma_per_sec_measured': fma_rate,
                     'cells_per_fma_slot': snp_cells_per_s / fma_rate if fma_rate else None},
             'stage_ms_per_step': {'rows_refine': tn['rows'][0] / args.steps, 'path': tn['path'][0] / args.steps,
@@ -479,6 +481,17 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ncu_traffic(reads_per_gpu):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one snp3_kernel launch from the committed ncu --set full capture
+    (profiles/snp_traffic.json, written by tools/ncu_traffic.py); null when the capture is for another batch size."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'snp_traffic.json')) as fh:
+            t = json.load(fh)
+        return t['dram_bytes_per_launch'] if t.get('reads_per_gpu') == reads_per_gpu else None
+    except (OSError, ValueError, KeyError):
+        return None
 
 
 def cpu_baseline(km, items, tweaked, args, mel):

@@ -128,7 +128,7 @@ struct LaneCfg {
 };
 
 __device__ __forceinline__ void lane_cfg_clear(LaneCfg &L) {
-  L.role = NVB_ROLE_IDLE; L.ws = -0x7fffffff - 1; L.we = 0x7fffffff; L.ms = 1; L.me = 0;
+  L.role = NVB_ROLE_IDLE; L.ws = -0x7fffffff - 1; L.we = 0x7fffffff; L.ms = 0x7fffffff; L.me = 0;  // empty B band
   L.mu = 0; L.ac = 0; L.mc = 0; L.cm = 0; L.abias = NVB_EZERO; L.pc = 0; L.kc = NVB_EZERO;
 }
 
@@ -158,7 +158,15 @@ struct LaneOut {
 // emission 1 on their B-row and their A-row cell multiplied by the closing suffix cell (sF, sX), which makes the B
 // cell the running sum of Node::TotalLikelihood (node.cpp:31-37), delayed by MEL steps; other lanes pass (1.0, 0).
 // `aout` receives the A-row cell (for callers that store it).
-template <int MEL, int MODE, bool WITH_JOIN>
+//
+// PH >= 0 = step index mod MEL: the A-row cells in flight to the B-row live in a ring (slot PH is the one pushed MEL
+// steps ago) for callers that unroll their step loop MEL times.  PH < 0: a plain shifting delay line for rolled loops.
+// Both kernels use PH < 0: unrolling saved ~6 register moves per step but cost registers -- the SNP kernel dropped
+// from 7 to 6 resident CTAs per SM and got 12 % slower (measured), the sweeps would lose their 14 CTAs per SM.
+// FWD_ONLY (forward-only callers with wobble rows): the A-row needs only its upper band limit (below the band its
+// inflow is already zero) and the B-row output only its lower one (above the band the consumer's own A-row limit cuts
+// it off); lanes without an output use ms = INT_MAX.  Measured neutral on the SNP kernel, so currently unused.
+template <int MEL, int MODE, bool WITH_JOIN, int PH, bool FWD_ONLY>
 __device__ __forceinline__ void lane_step(const LaneCfg &L, LaneState<MEL> &S, int c, double x, const LaneOut &in,
                                           double sF, int sX, LaneOut &out, XD &aout) {
   // own emission, reference formula ac - d*d*mc (kmer_model.cpp:47-51)
@@ -185,7 +193,8 @@ __device__ __forceinline__ void lane_step(const LaneCfg &L, LaneState<MEL> &S, i
       mix.e += L.abias;
     }
     S.w = xd_add(xd_make(mix.f * S.w.f, S.w.e + mix.e), pm);
-    wout = (c >= L.ws && c <= L.we) ? S.w : xd_zero();
+    const bool ina = (FWD_ONLY && MODE == NVB_MODE_WOBBLE) ? (c <= L.we) : (c >= L.ws && c <= L.we);
+    wout = ina ? S.w : xd_zero();
   }
   aout = wout;
 
@@ -205,13 +214,18 @@ __device__ __forceinline__ void lane_step(const LaneCfg &L, LaneState<MEL> &S, i
   } else {
 #pragma unroll
     for (int i = 0; i < MEL; i++) { S.q[i].f *= pb; S.q[i].e += kb; }
-    popped = S.q[MEL - 1];
+    if (PH >= 0) {  // ring: slot PH was pushed MEL steps ago
+      popped = S.q[PH >= 0 ? PH : 0];
+      S.q[PH >= 0 ? PH : 0] = push;
+    } else {        // PH < 0: plain delay line (callers that do not unroll their step loop)
+      popped = S.q[MEL - 1];
 #pragma unroll
-    for (int i = MEL - 1; i > 0; i--) S.q[i] = S.q[i - 1];
-    S.q[0] = push;
+      for (int i = MEL - 1; i > 0; i--) S.q[i] = S.q[i - 1];
+      S.q[0] = push;
+    }
   }
   S.mod = xd_add(xd_make(pb * S.mod.f, S.mod.e + kb), popped);
-  const bool inb = (c >= L.ms) && (c <= L.me);
+  const bool inb = (FWD_ONLY && MODE == NVB_MODE_WOBBLE) ? (c >= L.ms) : ((c >= L.ms) && (c <= L.me));
   out.f = inb ? S.mod.f : 0.0;
   out.E = inb ? S.mod.e : NVB_EZERO;
 }

@@ -207,7 +207,7 @@ __device__ void sweep_stripes(const ModelDev &M, const ReadView &v, double *F, i
       x1 = __ldg(v.sig + sample_index(t + 2));
       LaneOut in = shfl_up_out<MODE>(out);
       XD aout;
-      lane_step<MEL, MODE, false>(L, S, c, x, in, 1.0, 0, out, aout);
+      lane_step<MEL, MODE, false, -1, false>(L, S, c, x, in, 1.0, 0, out, aout);
       if (lane == 0) {
         const bool inb = (c >= L.ms && c <= L.me);
         out.f = inb ? 1.0 : 0.0;
@@ -251,7 +251,7 @@ __device__ void sweep_stripes(const ModelDev &M, const ReadView &v, double *F, i
 }
 
 template <int MEL, int MODE>
-__global__ void __launch_bounds__(256) sweep4_kernel(ModelDev M, BatchDev B, int b0, int n_items, int NW, int width,
+__global__ void __launch_bounds__(224, 4) sweep4_kernel(ModelDev M, BatchDev B, int b0, int n_items, int NW, int width,
                                                      const int64_t *mat_base, double *pF, int32_t *pX, double *sF,
                                                      int32_t *sX) {
   extern __shared__ unsigned long long smem_raw[];

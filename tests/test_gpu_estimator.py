@@ -176,3 +176,51 @@ def test_full_size_reads_properties_and_oracle(default_model):
         np.testing.assert_allclose(lls[0], want, rtol=1e-9)
         np.testing.assert_allclose((lls[0] - lls[0][0, args[0][1][0]]) / 10, (want - want[0, args[0][1][0]]) / 10,
                                    rtol=CHUNK_RTOL, atol=CHUNK_ATOL)
+
+
+def test_wide_band_and_long_read(default_model):
+    """Band-width sweep corner (BASELINE configs[4]): bandwidth 400 (801-column rows: several warps per sweep
+    direction, three chunks per row in the path search) against the oracle, and a 6000-base read with the default
+    band through size-independent properties (BASELINE configs[3] in miniature)."""
+    from nadavca_b200 import dtw, synthetic
+    from nadavca_b200.genome import Genome
+    from nadavca_b200.read import Read
+    from oracle import oracle as orc
+    km = default_model
+    genome = synthetic.make_genome(50_000, seed=9)
+    om = orc.OracleModel(6, 2, 4, km.mean, km.sigma, 'port')
+
+    def prepare(read, bw):
+        apx = synthetic.SyntheticAligner(genome).get_signal_alignment(read, bw)
+        s0, s1 = apx.signal_range
+        a, b = apx.read_sequence_range
+        return (read.normalized_signal[s0:s1], Genome.to_numerical(apx.reference_part),
+                Genome.to_numerical(read.sequence[a - 2:a]), Genome.to_numerical(read.sequence[b:b + 3]), apx.alignment)
+
+    wide = [synthetic.make_read(genome, km, 300 + i, n_bases=500 + 60 * i, bandwidth=400) for i in range(2)]
+    Read.normalize_reads(wide)
+    args = [prepare(r, 400) for r in wide]
+    with dtw.Batch(km, *[list(x) for x in zip(*args)], 400, 2) as batch:
+        assert max(int((be - bs + 1).max()) for bs, be in batch.bands()) > 704  # > 2 chunks of 352 columns
+        for flag in (True, False):
+            batch.refine(flag)
+            events, status = batch.events()
+            for ev, a in zip(events, args):
+                assert ev.tolist() == orc.refine_alignment(*a, 400, 2, om, flag)
+        batch.estimate(True)
+        lls, _ = batch.log_likelihoods()
+        want = np.array(orc.estimate_log_likelihoods(*args[0], 400, 2, om, True))
+        np.testing.assert_allclose(lls[0], want, rtol=1e-9)
+
+    long_read = [synthetic.make_read(genome, km, 400, n_bases=6000)]
+    Read.normalize_reads(long_read)
+    a = prepare(long_read[0], 150)
+    with dtw.Batch(km, *[[x] for x in a], 150, 2) as batch:
+        batch.refine(True)
+        events, status = batch.events()
+        ev = events[0]
+        assert status[0] == 0 and len(ev) == len(a[1])
+        assert np.all(ev[:, 1] - ev[:, 0] >= 2) and np.all(ev[1:, 0] >= ev[:-1, 1])
+        batch.estimate(True)
+        ll = batch.log_likelihoods()[0][0]
+        assert np.all(np.isfinite(ll)) and np.mean(np.argmax(ll, axis=1) == a[1]) > 0.97
