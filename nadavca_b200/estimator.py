@@ -367,7 +367,11 @@ def _device(kmer_model):
 
 
 def _dist(process_group):
+    """torch.distributed when the caller passed a process group, else None: collectives are never implied by an
+    initialised default group (a rank may well run a single-GPU estimate next to a distributed job)."""
+    if process_group is None:
+        return None
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and (process_group is not None or dist.get_world_size() > 1):
+    if dist.is_available() and dist.is_initialized():
         return dist
     return None
