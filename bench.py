@@ -137,6 +137,11 @@ class ClockSampler:
         self.index = index
         self.lines = []
         self.proc = None
+        self.first = 0
+
+    def mark(self):
+        """Start of the timed region: earlier samples are not summarised."""
+        self.first = len(self.lines)
 
     def __enter__(self):
         try:
@@ -165,7 +170,7 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for line in self.lines:
+        for line in self.lines[self.first:]:
             parts = [p.strip() for p in line.split(',')]
             if len(parts) < 7:
                 continue
@@ -363,15 +368,19 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    l0 = batch_n.launch_count + batch_t.launch_count
-    batch_n.enable_timing(True)
-    batch_t.enable_timing(True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # The sampler is started BEFORE the warm-up: the first nvidia-smi on a fresh box takes a second or two to attach
+    # to the driver and slows kernel launches while it does (measured: +20 ms per step on the first run of a box);
+    # only the samples taken during the timed region are summarised.
     with ClockSampler(local_rank) as clocks:
+        for _ in range(args.warmup):
+            step()
         barrier()
+        l0 = batch_n.launch_count + batch_t.launch_count
+        batch_n.enable_timing(True)
+        batch_t.enable_timing(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        clocks.mark()
         e0.record(stream)
         for _ in range(args.steps):
             out = step()
