@@ -98,7 +98,7 @@ struct Handoff {
 };
 
 template <int MEL, int MODE, bool REV>
-__device__ void sweep_stripes(const ModelDev &M, const ReadView &v, double *F, int32_t *X, int lane, int warp, int NW,
+__device__ __forceinline__ void sweep_stripes(const ModelDev &M, const ReadView &v, double *F, int32_t *X, int lane, int warp, int NW,
                               const Handoff &H, const StoreTile &tileB, const StoreTile &tileA) {
   constexpr int mode = MODE;
   const int n = v.n, N = v.N;
@@ -194,10 +194,14 @@ __device__ void sweep_stripes(const ModelDev &M, const ReadView &v, double *F, i
       // divergence around the shuffles) makes sure the producer is at least 16 cells ahead of that, sleeping otherwise.
       if (s > 0 && (t & 15) == 0 && (unsigned)t < row_cells) {
         const unsigned need = min((unsigned)t + 16u, row_cells);
+        unsigned backoff = 256;  // ns; a stripe starts ~340 producer steps (~200 us) before its first cell exists
         while (ready < need) {
           const unsigned long long w = H.word[in_buf];
           ready = ((w >> 32) == (in_tag >> 32)) ? (unsigned)w : 0u;
-          if (ready < need) __nanosleep(256);
+          if (ready < need) {
+            __nanosleep(backoff);
+            backoff = min(backoff * 2, 4096u);
+          }
         }
       }
       const int c = REV ? C0 - (t - lane) : C0 + (t - lane);
