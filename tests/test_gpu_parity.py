@@ -223,3 +223,40 @@ def test_workspace_waves_give_identical_results(default_model):
         assert np.array_equal(a, b)
     for a, b in zip(out[0][1], out[1][1]):
         assert np.array_equal(a, b)
+
+
+def test_batches_of_one_model_share_the_workspace(lib_built):
+    """The DP workspace belongs to the model: interleaved runs on two batches must not disturb each other's resident
+    results, and nvb_trim_memory must leave live batches intact."""
+    from nadavca_b200 import _cabi, dtw
+    rng = np.random.default_rng(21)
+    k, cp, mel, bw = 3, 1, 2, 9
+    mean = rng.normal(0, 1.2, size=64)
+    sigma = rng.uniform(0.2, 0.6, size=64)
+    gm = dtw.KmerModel(k, cp, 4, mean, sigma)
+
+    def lists(cases):
+        return [[c[i] for c in cases] for i in (2, 3, 4, 5, 6)]
+    small = [make_case(rng, k, cp, int(rng.integers(10, 30)), bw, mel) for _ in range(3)]
+    big = [make_case(rng, k, cp, int(rng.integers(60, 90)), bw, mel) for _ in range(5)]
+    with dtw.Batch(gm, *lists(small), bw, mel) as a, dtw.Batch(gm, *lists(big), bw, mel) as b:
+        a.refine(True)
+        ev_a = [e.copy() for e in a.events()[0]]
+        b.estimate(True)                      # grows and overwrites the shared workspace
+        ll_b = [x.copy() for x in b.log_likelihoods()[0]]
+        a.estimate(True)
+        ll_a = [x.copy() for x in a.log_likelihoods()[0]]
+        b.refine(True)
+        assert _cabi.load().nvb_trim_memory(gm.device) == 0
+        for x, y in zip(a.events()[0], ev_a):          # resident results of `a` survived b's runs and the trim
+            assert np.array_equal(x, y)
+        for x, y in zip(b.log_likelihoods()[0], ll_b):
+            assert np.array_equal(x, y)
+    # the same work on fresh, separate batches gives identical numbers
+    with dtw.Batch(gm, *lists(small), bw, mel) as a2:
+        a2.estimate(True)
+        for x, y in zip(a2.log_likelihoods()[0], ll_a):
+            assert np.array_equal(x, y)
+        a2.refine(True)
+        for x, y in zip(a2.events()[0], ev_a):
+            assert np.array_equal(x, y)
