@@ -260,3 +260,74 @@ def test_batches_of_one_model_share_the_workspace(lib_built):
         a2.refine(True)
         for x, y in zip(a2.events()[0], ev_a):
             assert np.array_equal(x, y)
+
+
+def test_empty_and_degenerate_batches(lib_built):
+    """Ragged corners: an empty batch, a read with an empty reference next to normal reads."""
+    from nadavca_b200 import dtw
+    rng = np.random.default_rng(31)
+    k, cp, mel, bw = 2, 1, 2, 6
+    mean = rng.normal(0, 1.2, size=16)
+    sigma = rng.uniform(0.2, 0.6, size=16)
+    gm = dtw.KmerModel(k, cp, 4, mean, sigma)
+    with dtw.Batch(gm, [], [], [], [], [], bw, mel) as batch:
+        batch.refine(True)
+        assert batch.events()[0] == []
+        batch.estimate(True)
+        assert batch.log_likelihoods()[0] == []
+    good = make_case(rng, k, cp, 25, bw, mel)
+    lists = [[good[i], np.zeros(0)] for i in (2, 3, 4, 5)] + [[good[6], np.zeros((0, 2), dtype=int)]]
+    lists[0][1] = rng.normal(0, 1, 7)  # a signal without any reference base
+    with dtw.Batch(gm, *lists, bw, mel) as batch:
+        batch.refine(False)
+        events, status = batch.events()
+        assert status.tolist() == [0, 2] and events[1] is None and events[0] is not None
+        batch.estimate(True)
+        lls, status = batch.log_likelihoods()
+        assert status.tolist() == [0, 2] and lls[1].shape == (0, 4) and np.all(np.isfinite(lls[0]))
+
+
+@pytest.mark.parametrize('mel', [4, 6])
+def test_long_minimum_event_lengths(lib_built, mel):
+    from nadavca_b200 import dtw
+    from oracle import oracle as orc
+    rng = np.random.default_rng(40 + mel)
+    k, cp, bw = 3, 1, 12
+    mean = rng.normal(0, 1.2, size=64)
+    sigma = rng.uniform(0.2, 0.6, size=64)
+    cases = [make_case(rng, k, cp, int(rng.integers(15, 50)), bw, mel, spacing=9) for _ in range(4)]
+    _compare_batch(rng, [(mean, sigma) + c[2:] for c in cases], k, cp, mel, bw, mean, sigma)
+    gm = dtw.KmerModel(k, cp, 4, mean, sigma)
+    with pytest.raises(dtw.NadavcaCudaError):
+        dtw.Batch(gm, [cases[0][2]], [cases[0][3]], [[]], [[]], [cases[0][6]], bw, 7)
+
+
+@pytest.mark.parametrize('k,cp', [(8, 3), (10, 4)])
+def test_large_kmer_models(lib_built, k, cp):
+    """k-mer tables beyond the shipped 6-mer (the reference's default model is a 10-mer, 4^10 entries = 25 MB of
+    tables): k+2 lanes per SNP task, 3 (k=8) or 2 (k=10) tasks per warp."""
+    rng = np.random.default_rng(50 + k)
+    mel, bw = 2, 10
+    mean = rng.normal(0, 1.2, size=4 ** k)
+    sigma = rng.uniform(0.25, 0.5, size=4 ** k)
+    cases = [make_case(rng, 3, 1, int(rng.integers(20, 45)), bw, mel) for _ in range(3)]
+
+    def with_model(c):
+        # make_case built the signal from its own small model; re-simulate the levels from the large one
+        ref = c[3]
+        n = len(ref)
+        padded = np.zeros(n + k, dtype=int)
+        padded[cp:cp + n] = ref
+        ids = np.zeros(n, dtype=int)
+        for j in range(k):
+            ids = ids * 4 + padded[j:j + n]
+        lengths = np.maximum(mel, rng.poisson(6, size=n))
+        starts = np.concatenate([[0], np.cumsum(lengths)[:-1]]) + bw
+        sig = np.concatenate([rng.normal(0, 1, bw), np.repeat(mean[ids], lengths) + rng.normal(0, 0.3, lengths.sum()),
+                              rng.normal(0, 1, bw)])
+        anchors = np.stack([np.clip(starts + rng.integers(-2, 3, size=n), 0, len(sig) - 1), np.arange(n)], axis=1)
+        anchors[:, 0] = np.maximum.accumulate(anchors[:, 0])
+        cb = rng.integers(0, 4, size=cp)
+        ca = rng.integers(0, 4, size=k - cp - 1)
+        return (mean, sigma, np.clip(sig, -5, 5), ref, cb, ca, anchors)
+    _compare_batch(rng, [with_model(c) for c in cases], k, cp, mel, bw, mean, sigma)
