@@ -143,7 +143,8 @@ int nvb_measure_fp64_fma_rate(int device, double *fma_per_second);
 int nvb_batch_get_alignment_table(nvb_batch *batch, const int64_t *start_in_signal, const int64_t *ref_start,
                                   const int64_t *ref_end, const int32_t *reverse, int64_t *out);
 /* _normalize_log_likelihoods + reverse-strand complement/flip (estimator.py:45-47,111-119) applied to the
- * resident raw log-likelihoods; d_chunks: double[sum n][4] device buffer (alphabet must be 4). */
+ * resident raw log-likelihoods; d_chunks: double[sum n][4] device buffer (alphabet must be 4).  Asynchronous: the
+ * per-read `reverse` (and `dest` below) arrays are kept on the device and re-uploaded only when they change. */
 int nvb_batch_chunk_values(nvb_batch *batch, const int32_t *reverse, double normalization_event_length,
                            double *d_chunks, void *stream);
 /* consensus accumulation (estimator.py:226-231): d_acc[dest[r] + i][j] += chunk_r[i][j], d_cov[dest[r]+i] += 1
@@ -154,6 +155,10 @@ int nvb_batch_scatter_add(nvb_batch *batch, const double *d_chunks, const int64_
  * (0..3, anything else = no base matches), group_off HOST int64[n_groups+1]; d_out double[total][4]. */
 int nvb_posterior(int device, const double *d_ll, const int8_t *d_ref, const int64_t *group_off,
                   int32_t n_groups, int k, double snp_prior, double *d_out, void *stream);
+/* the same with the group offsets already on the device (int64[n_groups+1], total = d_group_off[n_groups]): no upload
+ * and no synchronisation, the call only enqueues the kernel on `stream` */
+int nvb_posterior_d(int device, const double *d_ll, const int8_t *d_ref, const int64_t *d_group_off,
+                    int32_t n_groups, int64_t total, int k, double snp_prior, double *d_out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -79,6 +79,9 @@ SIGNATURES = {
                                              ctypes.c_void_p, ctypes.c_void_p]),
     'nvb_posterior': (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, c_i64p, ctypes.c_int32,
                                      ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
+    'nvb_posterior_d': (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                       ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p,
+                                       ctypes.c_void_p]),
 }
 
 _lib = None

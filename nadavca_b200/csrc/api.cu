@@ -156,6 +156,12 @@ struct nvb_batch {
   DevBuf<int32_t> d_events, d_status;
   DevBuf<double> d_ll;
   bool have_events = false, have_ll = false;
+  // small per-read arrays of the post-processing calls, kept on the device so that those calls need no
+  // synchronisation (re-uploaded only when the host values change)
+  DevBuf<int32_t> d_rev;
+  DevBuf<int64_t> d_dest;
+  std::vector<int32_t> h_rev;
+  std::vector<int64_t> h_dest;
   // per-read offsets into the model's DP workspace, valid for the last run
   DevBuf<int64_t> d_mat_base, d_dp_base, d_rec_base;
   int64_t ws_limit = 0;
@@ -754,12 +760,16 @@ int nvb_batch_chunk_values(nvb_batch *b, const int32_t *reverse, double normaliz
   if (b->model->dev.alphabet != 4) return fail(NVB_EINVAL, "chunk values need alphabet_size == 4");
   CU(cudaSetDevice(b->model->device));
   cudaStream_t st = (cudaStream_t)stream;
-  DevBuf<int32_t> d_rev;
-  CU(upload(d_rev, reverse, (size_t)b->n_reads, st));
-  nvbk_chunk_values(b->dev, b->d_ll.p, d_rev.p, normalization_event_length, b->total_ref, d_chunks, st);
+  const size_t n = (size_t)b->n_reads;
+  if (b->h_rev.size() != n || !std::equal(reverse, reverse + n, b->h_rev.begin())) {
+    CU(cudaStreamSynchronize(st));  // an earlier launch may still read the old values
+    b->h_rev.assign(reverse, reverse + n);
+    CU(upload(b->d_rev, b->h_rev.data(), n, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  nvbk_chunk_values(b->dev, b->d_ll.p, b->d_rev.p, normalization_event_length, b->total_ref, d_chunks, st);
   b->launches++;
   CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(st));  // d_rev is freed on return
   return NVB_OK;
 }
 
@@ -768,12 +778,26 @@ int nvb_batch_scatter_add(nvb_batch *b, const double *d_chunks, const int64_t *d
   if (!b || !d_chunks || !dest || !d_acc || !d_cov) return fail(NVB_EINVAL, "NULL argument");
   CU(cudaSetDevice(b->model->device));
   cudaStream_t st = (cudaStream_t)stream;
-  DevBuf<int64_t> d_dest;
-  CU(upload(d_dest, dest, (size_t)b->n_reads, st));
-  nvbk_scatter_add(b->dev, d_chunks, d_dest.p, b->d_status.p, b->total_ref, d_acc, d_cov, st);
+  const size_t n = (size_t)b->n_reads;
+  if (b->h_dest.size() != n || !std::equal(dest, dest + n, b->h_dest.begin())) {
+    CU(cudaStreamSynchronize(st));
+    b->h_dest.assign(dest, dest + n);
+    CU(upload(b->d_dest, b->h_dest.data(), n, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  nvbk_scatter_add(b->dev, d_chunks, b->d_dest.p, b->d_status.p, b->total_ref, d_acc, d_cov, st);
   b->launches++;
   CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(st));
+  return NVB_OK;
+}
+
+int nvb_posterior_d(int device, const double *d_ll, const int8_t *d_ref, const int64_t *d_group_off, int32_t n_groups,
+                    int64_t total, int k, double snp_prior, double *d_out, void *stream) {
+  if (!d_ll || !d_ref || !d_group_off || !d_out || n_groups < 0 || total < 0) return fail(NVB_EINVAL, "bad argument");
+  if (nvb_device_count() <= device) return fail(NVB_ECUDA, "CUDA device %d not available (no CPU fallback)", device);
+  CU(cudaSetDevice(device));
+  nvbk_posterior(d_ll, d_ref, d_group_off, n_groups, total, k, snp_prior, d_out, (cudaStream_t)stream);
+  CU(cudaGetLastError());
   return NVB_OK;
 }
 

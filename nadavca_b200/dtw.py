@@ -273,6 +273,14 @@ def posterior(device, d_ll, d_ref, group_off, k, snp_prior, d_out, stream=None):
                                   ctypes.c_void_p(d_out), _stream(stream)), 'nvb_posterior')
 
 
+def posterior_resident(device, d_ll, d_ref, d_group_off, n_groups, total, k, snp_prior, d_out, stream=None):
+    """_compute_posterior with the group offsets already on the device: enqueues the kernel, no synchronisation."""
+    lib = _cabi.require_device()
+    _cabi.check(lib.nvb_posterior_d(int(device), ctypes.c_void_p(d_ll), ctypes.c_void_p(d_ref),
+                                    ctypes.c_void_p(d_group_off), int(n_groups), int(total), int(k), float(snp_prior),
+                                    ctypes.c_void_p(d_out), _stream(stream)), 'nvb_posterior_d')
+
+
 # ---- the two functions of the reference module, one read per call ------------------------------------------
 
 def refine_alignment(signal, reference, context_before, context_after, approximate_alignment, bandwidth,

@@ -279,7 +279,8 @@ class ProbabilityEstimator:
             plan = self.plan_groups(intervals, reference, independent, process_group)
         if plan is None:
             return None
-        groups, group_off, dest, d_ref = plan
+        groups, group_off, dest, d_ref = plan[:4]
+        d_group_off = plan[4] if len(plan) > 4 else torch.as_tensor(group_off, device=dev)
         total = int(group_off[-1])
         acc = torch.zeros((total, 4), dtype=torch.float64, device=dev)
         cov = torch.zeros(total, dtype=torch.int32, device=dev)
@@ -291,8 +292,8 @@ class ProbabilityEstimator:
             dist.all_reduce(acc, group=process_group)  # the one exchange step (estimator.py:228-231)
             dist.all_reduce(cov, group=process_group)
         out = torch.empty_like(acc)
-        dtw.posterior(dev.index, acc.data_ptr(), d_ref.data_ptr(), group_off, self.kmer_model.get_k(),
-                      self.snp_prior, out.data_ptr(), stream)
+        dtw.posterior_resident(dev.index, acc.data_ptr(), d_ref.data_ptr(), d_group_off.data_ptr(), len(groups), total,
+                               self.kmer_model.get_k(), self.snp_prior, out.data_ptr(), stream)
         return groups, group_off, out, cov
 
     def plan_groups(self, intervals, reference, independent=False, process_group=None):
@@ -306,7 +307,8 @@ class ProbabilityEstimator:
         groups, group_off, dest = host
         ref_codes = numpy.concatenate([_ref_codes(reference[g[0]:g[1]]) for g in groups])
         d_ref = torch.as_tensor(ref_codes, device=dev)
-        return groups, group_off, dest, d_ref
+        d_group_off = torch.as_tensor(group_off, device=dev)
+        return groups, group_off, dest, d_ref, d_group_off
 
 
 def plan_groups_host(intervals, independent=False, process_group=None):
