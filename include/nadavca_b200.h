@@ -142,6 +142,11 @@ int nvb_measure_fp64_fma_rate(int device, double *fma_per_second);
  * reference position = ref_start + i (forward) or ref_end - i - 1 (reverse strand). Host buffers. */
 int nvb_batch_get_alignment_table(nvb_batch *batch, const int64_t *start_in_signal, const int64_t *ref_start,
                                   const int64_t *ref_end, const int32_t *reverse, int64_t *out);
+/* Mean of the signal samples of every refined event, out double[sum n] (host): the numpy.mean calls of
+ * Read.tweak_signal_normalization (read.py:86) and of the align_signal renormalisation (align_signal.py:66-70),
+ * reproduced bit for bit (numpy's pairwise summation order) from the resident signal and events.  NaN for reads
+ * without a path and for empty events. */
+int nvb_batch_event_means(nvb_batch *batch, double *out);
 /* _normalize_log_likelihoods + reverse-strand complement/flip (estimator.py:45-47,111-119) applied to the
  * resident raw log-likelihoods; d_chunks: double[sum n][4] device buffer (alphabet must be 4).  Asynchronous: the
  * per-read `reverse` (and `dest` below) arrays are kept on the device and re-uploaded only when they change. */

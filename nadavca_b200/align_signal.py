@@ -35,14 +35,18 @@ def load_model_and_estimator(reference_filename, config=defaults.CONFIG_FILE, km
     return kmer_model, ProbabilityEstimator(kmer_model, aligner, config)
 
 
-def _linear_renormalization(kmer_model, read, apx_alignment, alignment):
+def _linear_renormalization(kmer_model, read, apx_alignment, alignment, signal_means=None, expected=None):
     """One even renorm round (align_signal.py:59-76): regress per-event means on the expected levels and rescale
-    the whole normalised signal."""
-    bases_num = Genome.to_numerical(apx_alignment.reference_part)
-    expected = np.array(kmer_model.get_expected_signal(bases_num, [], []))
-    signal_cut = read.normalized_signal[alignment[0][1]:alignment[-1][2]]
-    al_start = alignment[0][1]
-    signal_means = [np.mean(signal_cut[s - al_start:e - al_start]) for _, s, e in alignment]
+    the whole normalised signal.  `signal_means` are the device-computed event means (bit-identical to the
+    reference's per-event numpy.mean loop) and `expected` the expected levels with EMPTY contexts
+    (align_signal.py:63); without them both are computed here, one read at a time."""
+    if expected is None:
+        bases_num = Genome.to_numerical(apx_alignment.reference_part)
+        expected = np.array(kmer_model.get_expected_signal(bases_num, [], []))
+    if signal_means is None:
+        signal_cut = read.normalized_signal[alignment[0][1]:alignment[-1][2]]
+        al_start = alignment[0][1]
+        signal_means = [np.mean(signal_cut[s - al_start:e - al_start]) for _, s, e in alignment]
     slope, intercept, _, _, _ = linregress(expected, signal_means)
     read.normalized_signal = (read.normalized_signal - intercept) / slope
 
@@ -70,15 +74,17 @@ def align_signal(reference_filename,
         if isinstance(read, str):
             reads[i] = Read.load_from_fast5(read, group_name)
         Read.normalize_reads([reads[i]])  # per-read median/MAD (align_signal.py:54)
-    results = estimator.get_refined_alignments(reads)
+    results = estimator.get_refined_alignments(reads, with_event_means=True)
     for r in range(renorm_rounds):
         alive = [i for i, res in enumerate(results) if res is not None]
         if r % 2 == 0:
-            for i in alive:
-                _linear_renormalization(kmer_model, reads[i], *results[i])
+            refs = [Genome.to_numerical(results[i][0].reference_part) for i in alive]
+            expected = kmer_model.get_expected_signal_batch(refs, [[]] * len(alive), [[]] * len(alive))
+            for i, exp in zip(alive, expected):
+                _linear_renormalization(kmer_model, reads[i], *results[i], expected=exp)
         else:
-            again = estimator.get_refined_alignments([reads[i] for i in alive])
+            again = estimator.get_refined_alignments([reads[i] for i in alive], with_event_means=True)
             for i, res in zip(alive, again):
                 results[i] = res
     for read, res in zip(reads, results):
-        yield read, res
+        yield read, (None if res is None else res[:2])

@@ -753,6 +753,19 @@ int nvb_batch_get_alignment_table(nvb_batch *b, const int64_t *start_in_signal, 
   return NVB_OK;
 }
 
+int nvb_batch_event_means(nvb_batch *b, double *out) {
+  if (!b || !out) return fail(NVB_EINVAL, "NULL argument");
+  if (!b->have_events) return fail(NVB_ESTATE, "event means requested before nvb_batch_refine");
+  CU(cudaSetDevice(b->model->device));
+  DevBuf<double> d_out;
+  CU(d_out.alloc((size_t)b->total_ref));
+  nvbk_event_means(b->dev, b->d_events.p, b->d_status.p, b->total_ref, d_out.p, 0);
+  b->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out, d_out.p, (size_t)b->total_ref * sizeof(double), cudaMemcpyDeviceToHost));
+  return NVB_OK;
+}
+
 int nvb_batch_chunk_values(nvb_batch *b, const int32_t *reverse, double normalization_event_length, double *d_chunks,
                            void *stream) {
   if (!b || !reverse || !d_chunks) return fail(NVB_EINVAL, "NULL argument");

@@ -28,6 +28,50 @@ __global__ void alignment_table_kernel(BatchDev B, const int32_t *events, const 
   out[3 * g + 2] = events[2 * g + 1] + sig_start[b];
 }
 
+// numpy's float64 add.reduce over a contiguous 1-D array (pairwise_sum in numpy/_core/src/umath/loops_utils.h.src):
+// fewer than 8 terms are added in order, up to 128 terms go through 8 interleaved accumulators combined as
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus an in-order tail, longer blocks are split at n/2 rounded down to a multiple
+// of 8.  Reproduced operation for operation (the file is compiled without FMA contraction) so that event means equal
+// numpy.mean bit for bit -- they feed the spline tweak (read.py:86-88) and the linear renormalisation
+// (align_signal.py:66-72), whose results the alignment must match exactly.
+__device__ double numpy_pairwise_sum(const double *a, int n) {
+  if (n < 8) {
+    double res = 0.0;
+    for (int i = 0; i < n; i++) res += a[i];
+    return res;
+  }
+  if (n <= 128) {
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) r[j] = a[j];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) r[j] += a[i + j];
+    }
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; i++) res += a[i];
+    return res;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return numpy_pairwise_sum(a, n2) + numpy_pairwise_sum(a + n2, n - n2);
+}
+
+// Mean of the signal samples of every refined event (read.py:86, align_signal.py:66-70): one thread per base.
+__global__ void event_means_kernel(BatchDev B, const int32_t *events, const int32_t *status, int64_t total,
+                                   double *out) {
+  int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const int b = find_read(B, g);
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  if (status[b] != 0) { out[g] = nan; return; }
+  const int s = events[2 * g], e = events[2 * g + 1];
+  const int n = e - s;
+  if (n <= 0) { out[g] = nan; return; }  // numpy.mean of an empty slice
+  out[g] = numpy_pairwise_sum(B.signal + B.sig_off[b] + s, n) / (double)n;
+}
+
 // (LL - LL[0][ref[0]]) / normalization_event_length; reverse strand: complement the columns, flip the rows.
 __global__ void chunk_values_kernel(BatchDev B, const double *ll, const int32_t *reverse, double nel, int64_t total,
                                     double *chunks) {
@@ -125,6 +169,11 @@ void nvbk_alignment_table(const BatchDev &B, const int32_t *d_events, const int3
   if (total > 0)
     alignment_table_kernel<<<blocks_for(total), 256, 0, st>>>(B, d_events, d_status, d_sig_start, d_ref_start,
                                                               d_ref_end, d_reverse, total, d_out);
+}
+
+void nvbk_event_means(const BatchDev &B, const int32_t *d_events, const int32_t *d_status, int64_t total, double *d_out,
+                      cudaStream_t st) {
+  if (total > 0) event_means_kernel<<<blocks_for(total), 256, 0, st>>>(B, d_events, d_status, total, d_out);
 }
 
 void nvbk_chunk_values(const BatchDev &B, const double *d_ll, const int32_t *d_reverse, double nel, int64_t total,

@@ -33,6 +33,8 @@ int nvbk_path2(const BatchDev &B, int mode, int b0, int b1, const int64_t *d_mat
 void nvbk_alignment_table(const BatchDev &B, const int32_t *d_events, const int32_t *d_status,
                           const int64_t *d_sig_start, const int64_t *d_ref_start, const int64_t *d_ref_end,
                           const int32_t *d_reverse, int64_t total, int64_t *d_out, cudaStream_t st);
+void nvbk_event_means(const BatchDev &B, const int32_t *d_events, const int32_t *d_status, int64_t total, double *d_out,
+                      cudaStream_t st);
 void nvbk_chunk_values(const BatchDev &B, const double *d_ll, const int32_t *d_reverse, double nel, int64_t total,
                        double *d_chunks, cudaStream_t st);
 void nvbk_scatter_add(const BatchDev &B, const double *d_chunks, const int64_t *d_dest, const int32_t *d_status,

@@ -209,6 +209,15 @@ class Batch:
         return [out[off[i]:off[i + 1]] if (off[i + 1] > off[i] and out[off[i], 1] >= 0) else None
                 for i in range(self.n_reads)]
 
+    def event_means(self):
+        """Per read: mean signal level of every refined event (bit-identical to numpy.mean over the event's samples);
+        NaN rows for reads without a path."""
+        out = np.zeros(self.pack.total_reference, dtype=np.float64)
+        _cabi.check(self.lib.nvb_batch_event_means(self.handle, _cabi.ptr(out, ctypes.c_double)),
+                    'nvb_batch_event_means')
+        off = self.pack.reference_off
+        return [out[off[i]:off[i + 1]] for i in range(self.n_reads)]
+
     def chunk_values(self, reverse, normalization_event_length, d_chunks, stream=None):
         """Normalised, strand-corrected chunk values into the device buffer `d_chunks` (a data pointer)."""
         r = _cabi.as_array(reverse, np.int32)

@@ -146,9 +146,11 @@ class ProbabilityEstimator:
                          workspace_limit=self.workspace_limit)
 
     # ---- path A: refined alignments ---------------------------------------------------------------------------
-    def get_refined_alignments(self, reads):
+    def get_refined_alignments(self, reads, with_event_means=False):
         """Batched get_refined_alignment: list (one per read) of (ApproximateSignalAlignment, int (n,3) array) or
-        None for reads that are unaligned or have no valid path."""
+        None for reads that are unaligned or have no valid path.  With `with_event_means` every result carries a third
+        item, the mean signal level of each event (``numpy.mean(normalized_signal[start:end])`` bit for bit, computed
+        on the device) -- what the renormalisation rounds of align_signal need (align_signal.py:66-70)."""
         prepared = [self._prepare(read) for read in reads]
         items = [it for it in prepared if it is not None]
         results = [None] * len(reads)
@@ -161,15 +163,16 @@ class ProbabilityEstimator:
                                             [it.apx.reference_range[0] for it in items],
                                             [it.apx.reference_range[1] for it in items],
                                             [int(it.apx.reverse_complement) for it in items])
+            means = batch.event_means() if with_event_means else None
             self.last_stats = {'launches': batch.launch_count}
         pos = 0
         for i, it in enumerate(prepared):
             if it is None:
                 continue
             table = tables[pos]
-            pos += 1
             if table is not None:
-                results[i] = (it.apx, table.astype(int))
+                results[i] = (it.apx, table.astype(int)) + ((means[pos].copy(),) if with_event_means else ())
+            pos += 1
         return results
 
     def get_refined_alignment(self, read):
@@ -193,7 +196,9 @@ class ProbabilityEstimator:
                                                                  [it.context_before for it in items],
                                                                  [it.context_after for it in items])
             keep = [i for i, ev in enumerate(events) if ev is not None]
+            event_means = batch.event_means()  # per-event signal means, computed next to the resident events
             if len(keep) != len(items):
+                event_means = [event_means[i] for i in keep]
                 batch.close()
                 items = [items[i] for i in keep]
                 events = [events[i] for i in keep]
@@ -202,8 +207,8 @@ class ProbabilityEstimator:
                     return [], None
                 signals = [signals[i] for i in keep]
                 batch = self._batch(items, signals)
-            for it, ev, exp_sig in zip(items, events, expected):
-                it.read.tweak_signal_normalization(ev.astype(int) + it.signal_range[0], exp_sig)
+            for it, ev, exp_sig, means in zip(items, events, expected, event_means):
+                it.read.tweak_signal_normalization(ev.astype(int) + it.signal_range[0], exp_sig, means.tolist())
             batch.set_signals([it.read.tweaked_normalized_signal[it.signal_range[0]:it.signal_range[1]]
                                for it in items])
         batch.estimate(self.model_wobbling)

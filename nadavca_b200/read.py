@@ -46,11 +46,16 @@ class Read:
         for read in reads:
             read.normalized_signal = numpy.clip((read.raw_signal - shift) / scale, -5, 5)
 
-    def tweak_signal_normalization(self, alignment, expected_means):
-        """Cubic smoothing spline from observed event means to expected levels (read.py:83-94)."""
+    def tweak_signal_normalization(self, alignment, expected_means, event_means=None):
+        """Cubic smoothing spline from observed event means to expected levels (read.py:83-94).
+
+        `event_means` (optional) are the per-event means of ``normalized_signal`` already computed on the device by
+        ``dtw.Batch.event_means`` -- bit-identical to the ``numpy.mean`` calls of the reference's per-event Python
+        loop, which at ~2000 events per read is the dominant host cost of ``estimate_snps``."""
+        if event_means is None:
+            event_means = [numpy.mean(self.normalized_signal[event[0]: event[1]]) for event in alignment]
         data = []
-        for event, expected_mean in zip(alignment, expected_means):
-            mean = numpy.mean(self.normalized_signal[event[0]: event[1]])
+        for mean, expected_mean in zip(event_means, expected_means):
             if abs(expected_mean - mean) <= 1:
                 data.append((mean, expected_mean))
         data.sort()

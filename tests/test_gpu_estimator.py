@@ -224,3 +224,37 @@ def test_wide_band_and_long_read(default_model):
         batch.estimate(True)
         ll = batch.log_likelihoods()[0][0]
         assert np.all(np.isfinite(ll)) and np.mean(np.argmax(ll, axis=1) == a[1]) > 0.97
+
+
+def test_event_means_equal_numpy_mean_bit_for_bit(golden_estimator, default_model):
+    """nvb_batch_event_means reproduces numpy.mean (pairwise summation order) exactly, including events longer than
+    8 and 128 samples and reads without a path."""
+    from nadavca_b200 import dtw
+    rng = np.random.default_rng(77)
+    k, cp, mel, bw = 2, 1, 2, 40
+    mean = rng.normal(0, 1.2, size=16)
+    sigma = rng.uniform(0.2, 0.5, size=16)
+    gm = dtw.KmerModel(k, cp, 4, mean, sigma)
+    cases = [make_case_local(rng, k, cp, n, bw, mel, spacing) for n, spacing in ((30, 6), (8, 150), (20, 40), (12, 12))]
+    sig = rng.normal(0, 1, 12)
+    cases.append((sig, rng.integers(0, 4, 10), [], [], np.array([[0, 0], [11, 9]])))  # no path
+    lists = [[c[i] for c in cases] for i in range(5)]
+    with dtw.Batch(gm, *lists, bw, mel) as batch:
+        for flag in (False, True):
+            batch.refine(flag)
+            events, status = batch.events()
+            means = batch.event_means()
+            longest = 0
+            for ev, m, c in zip(events, means, cases):
+                if ev is None:
+                    assert np.all(np.isnan(m))
+                    continue
+                want = np.array([np.mean(c[0][s:e]) for s, e in ev])
+                assert np.array_equal(m, want)
+                longest = max(longest, int((ev[:, 1] - ev[:, 0]).max()))
+            assert longest > 128  # the recursive split of numpy's pairwise sum was exercised
+
+
+def make_case_local(rng, k, cp, n, bw, mel, spacing):
+    from conftest import make_case
+    return make_case(rng, k, cp, n, bw, mel, spacing=spacing)[2:]

@@ -200,3 +200,21 @@ def test_product_never_imports_oracle():
             if name.endswith(('.py', '.cu', '.cuh', '.h')):
                 text = open(os.path.join(dirpath, name), errors='replace').read()
                 assert 'import oracle' not in text and 'from oracle' not in text and 'oracle/' not in text, name
+
+
+def test_tweak_with_precomputed_event_means(golden_estimator):
+    """Read.tweak_signal_normalization gives the same spline whether the event means come from its own numpy.mean
+    loop (reference behaviour, read.py:83-94) or are passed in (the device-computed ones are bit-identical)."""
+    from nadavca_b200.read import Read
+    reads = golden_reads(golden_estimator)
+    Read.normalize_reads(reads)
+    r = reads[0]
+    table = golden_estimator['tweak1/read0/alignment_table']
+    events = table[:, 1:]
+    rng = np.random.default_rng(3)
+    expected = [float(np.mean(r.normalized_signal[s:e])) + rng.normal(0, 0.2) for s, e in events]
+    r.tweak_signal_normalization(events, expected)
+    a = r.tweaked_normalized_signal.copy()
+    means = [float(np.mean(r.normalized_signal[s:e])) for s, e in events]
+    r.tweak_signal_normalization(events, expected, means)
+    assert np.array_equal(a, r.tweaked_normalized_signal)
