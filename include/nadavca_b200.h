@@ -147,6 +147,14 @@ int nvb_batch_get_alignment_table(nvb_batch *batch, const int64_t *start_in_sign
  * reproduced bit for bit (numpy's pairwise summation order) from the resident signal and events.  NaN for reads
  * without a path and for empty events. */
 int nvb_batch_event_means(nvb_batch *batch, double *out);
+/* Evaluation half of Read.tweak_signal_normalization (read.py:94, scipy.interpolate.splev, FITPACK splev/fpbspl with
+ * extrapolation): every sample x of a read's resident signal is replaced by spline_r(x).  The splines come from the
+ * host fit (scipy.interpolate.splrep, read.py:93) as FITPACK's knots t and coefficients c, both of length
+ * spline_off[r+1] - spline_off[r] per read (0 = leave the read's signal as it is); degree = 3 for the reference. */
+int nvb_batch_apply_splines(nvb_batch *batch, const double *knots, const double *coefs, const int64_t *spline_off,
+                            int degree, void *stream);
+/* the resident signal values (after nvb_batch_set_signal / nvb_batch_apply_splines), double[signal_off[n_reads]] */
+int nvb_batch_get_signal(nvb_batch *batch, double *out);
 /* _normalize_log_likelihoods + reverse-strand complement/flip (estimator.py:45-47,111-119) applied to the
  * resident raw log-likelihoods; d_chunks: double[sum n][4] device buffer (alphabet must be 4).  Asynchronous: the
  * per-read `reverse` (and `dest` below) arrays are kept on the device and re-uploaded only when they change. */

@@ -74,6 +74,8 @@ SIGNATURES = {
     'nvb_measure_fp64_fma_rate': (ctypes.c_int, [ctypes.c_int, c_f64p]),
     'nvb_batch_get_alignment_table': (ctypes.c_int, [ctypes.c_void_p, c_i64p, c_i64p, c_i64p, c_i32p, c_i64p]),
     'nvb_batch_event_means': (ctypes.c_int, [ctypes.c_void_p, c_f64p]),
+    'nvb_batch_apply_splines': (ctypes.c_int, [ctypes.c_void_p, c_f64p, c_f64p, c_i64p, ctypes.c_int, ctypes.c_void_p]),
+    'nvb_batch_get_signal': (ctypes.c_int, [ctypes.c_void_p, c_f64p]),
     'nvb_batch_chunk_values': (ctypes.c_int, [ctypes.c_void_p, c_i32p, ctypes.c_double, ctypes.c_void_p,
                                               ctypes.c_void_p]),
     'nvb_batch_scatter_add': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_i64p, ctypes.c_void_p,

@@ -57,15 +57,33 @@ def base_mapping_from_cigar(cigar, mapped_position, read_sequence, reference, is
     return numpy.array(mapping, dtype=int).reshape(-1, 2)
 
 
+def _mapping_arrays(read):
+    """read.sequence_to_signal_mapping (a dict base index -> sample index) as sorted key / value arrays, cached on
+    the read (the dict itself is the reference's data contract, read.py:16)."""
+    cached = getattr(read, '_mapping_arrays', None)
+    mapping = read.sequence_to_signal_mapping
+    if cached is None or cached[2] is not mapping or cached[3] != len(mapping):
+        keys = numpy.fromiter(mapping.keys(), dtype=numpy.int64, count=len(mapping))
+        vals = numpy.fromiter(mapping.values(), dtype=numpy.int64, count=len(mapping))
+        order = numpy.argsort(keys, kind='stable')
+        cached = (keys[order], vals[order], mapping, len(mapping))
+        read._mapping_arrays = cached
+    return cached[0], cached[1]
+
+
 def signal_alignment_from_base_mapping(read, base_mapping, is_reverse_complement, contig_name, reference,
                                        bandwidth):
     """alignment.py:142-186: base anchors -> (signal index, reference index) anchors, ranges and reference part.
 
     `base_mapping` holds (index in read.sequence, index in the reference) pairs in read orientation -- for the
     reverse strand the reference index counts from the END of the contig, as the reference's CIGAR walk produces."""
-    mapping = read.sequence_to_signal_mapping
-    pairs = [(mapping[int(r)], int(g)) for r, g in base_mapping if int(r) in mapping]  # convert_mapping, :58-63
-    signal_mapping = numpy.array(pairs, dtype=int).reshape(-1, 2)
+    # convert_mapping (alignment.py:58-63): bases the basecaller did not place in the signal are dropped
+    base_mapping = numpy.asarray(base_mapping, dtype=int).reshape(-1, 2)
+    keys, samples = _mapping_arrays(read)
+    pos = numpy.searchsorted(keys, base_mapping[:, 0])
+    pos[pos >= len(keys)] = 0
+    known = keys[pos] == base_mapping[:, 0] if len(keys) else numpy.zeros(len(base_mapping), dtype=bool)
+    signal_mapping = numpy.stack([samples[pos[known]], base_mapping[known, 1]], axis=1).astype(int).reshape(-1, 2)
     if len(signal_mapping) == 0:
         return None
     start_in_reference = signal_mapping[0][1]
@@ -84,6 +102,7 @@ def signal_alignment_from_base_mapping(read, base_mapping, is_reverse_complement
     return ApproximateSignalAlignment(alignment=signal_mapping,
                                       signal_range=(extended_start, extended_end),
                                       reference_range=(int(start_in_reference), int(end_in_reference)),
+                                      # the UNFILTERED base mapping gives the read range (alignment.py:173-175)
                                       read_sequence_range=(int(base_mapping[0][0]), int(base_mapping[-1][0]) + 1),
                                       reverse_complement=bool(is_reverse_complement),
                                       reference_part=reference_part,

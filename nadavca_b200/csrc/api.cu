@@ -766,6 +766,40 @@ int nvb_batch_event_means(nvb_batch *b, double *out) {
   return NVB_OK;
 }
 
+int nvb_batch_apply_splines(nvb_batch *b, const double *knots, const double *coefs, const int64_t *spline_off,
+                            int degree, void *stream) {
+  if (!b || !spline_off) return fail(NVB_EINVAL, "NULL argument");
+  if (degree < 1 || degree > 5) return fail(NVB_EINVAL, "spline degree must be 1..5");
+  int rc = check_offsets(spline_off, b->n_reads, "spline");
+  if (rc) return rc;
+  const int64_t total = spline_off[b->n_reads];
+  if (total > 0 && (!knots || !coefs)) return fail(NVB_EINVAL, "NULL argument");
+  for (int i = 0; i < b->n_reads; i++) {
+    const int64_t n = spline_off[i + 1] - spline_off[i];
+    if (n != 0 && n < 2 * (degree + 1)) return fail(NVB_EINVAL, "spline of read %d has %lld knots, needs %d", i, (long long)n, 2 * (degree + 1));
+  }
+  CU(cudaSetDevice(b->model->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  DevBuf<double> d_knots, d_coefs;
+  DevBuf<int64_t> d_off;
+  CU(upload(d_knots, knots, (size_t)total, st));
+  CU(upload(d_coefs, coefs, (size_t)total, st));
+  CU(upload(d_off, spline_off, (size_t)b->n_reads + 1, st));
+  nvbk_apply_splines(b->dev, b->d_signal.p, d_knots.p, d_coefs.p, d_off.p, degree, b->total_sig, st);
+  b->launches++;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(st));  // the temporaries go back to the block cache on return
+  return NVB_OK;
+}
+
+int nvb_batch_get_signal(nvb_batch *b, double *out) {
+  if (!b || !out) return fail(NVB_EINVAL, "NULL argument");
+  CU(cudaSetDevice(b->model->device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(out, b->d_signal.p, (size_t)b->total_sig * sizeof(double), cudaMemcpyDeviceToHost));
+  return NVB_OK;
+}
+
 int nvb_batch_chunk_values(nvb_batch *b, const int32_t *reverse, double normalization_event_length, double *d_chunks,
                            void *stream) {
   if (!b || !reverse || !d_chunks) return fail(NVB_EINVAL, "NULL argument");

@@ -72,6 +72,56 @@ __global__ void event_means_kernel(BatchDev B, const int32_t *events, const int3
   out[g] = numpy_pairwise_sum(B.signal + B.sig_off[b] + s, n) / (double)n;
 }
 
+// FITPACK splev (ext = 0) / fpbspl, degree k <= 5, for one abscissa: the evaluation half of
+// Read.tweak_signal_normalization (read.py:94, scipy.interpolate.splev).  Same operations in the same order as the
+// Fortran (no FMA contraction in this file), so the result equals scipy's up to the compiler's rounding of a/b.
+__device__ double fitpack_splev(const double *t, const double *c, int n, int k, double x) {
+  const int k1 = k + 1, nk1 = n - k1;
+  // l (1-based) = last knot <= x, clamped to [k1, nk1]
+  int lo = 0, hi = n;  // count of knots <= x
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (t[mid] <= x) lo = mid + 1; else hi = mid;
+  }
+  const int l = min(max(lo, k1), nk1);
+  double h[6], hh[5];
+  h[0] = 1.0;
+  for (int j = 1; j <= k; j++) {
+    for (int i = 0; i < j; i++) hh[i] = h[i];
+    h[0] = 0.0;
+    for (int i = 1; i <= j; i++) {
+      const int li = l + i, lj = li - j;  // 1-based knot indices
+      const double tli = t[li - 1], tlj = t[lj - 1];
+      if (tli == tlj) {
+        h[i] = 0.0;
+      } else {
+        const double f = hh[i - 1] / (tli - tlj);
+        h[i - 1] = h[i - 1] + f * (tli - x);
+        h[i] = f * (x - tlj);
+      }
+    }
+  }
+  double sp = 0.0;
+  for (int j = 1; j <= k1; j++) sp = sp + c[l - k1 + j - 1] * h[j - 1];
+  return sp;
+}
+
+// signal[g] <- spline_b(signal[g]) for every sample of every read that has a spline (n_knots > 0), in place.
+__global__ void apply_splines_kernel(BatchDev B, double *signal, const double *knots, const double *coefs,
+                                     const int64_t *spl_off, int degree, int64_t total) {
+  int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  int lo = 0, hi = B.n_reads;  // last read with sig_off <= g
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (B.sig_off[mid] <= g) lo = mid; else hi = mid;
+  }
+  const int64_t o = spl_off[lo];
+  const int n = (int)(spl_off[lo + 1] - o);
+  if (n < 2 * (degree + 1)) return;
+  signal[g] = fitpack_splev(knots + o, coefs + o, n, degree, signal[g]);
+}
+
 // (LL - LL[0][ref[0]]) / normalization_event_length; reverse strand: complement the columns, flip the rows.
 __global__ void chunk_values_kernel(BatchDev B, const double *ll, const int32_t *reverse, double nel, int64_t total,
                                     double *chunks) {
@@ -174,6 +224,12 @@ void nvbk_alignment_table(const BatchDev &B, const int32_t *d_events, const int3
 void nvbk_event_means(const BatchDev &B, const int32_t *d_events, const int32_t *d_status, int64_t total, double *d_out,
                       cudaStream_t st) {
   if (total > 0) event_means_kernel<<<blocks_for(total), 256, 0, st>>>(B, d_events, d_status, total, d_out);
+}
+
+void nvbk_apply_splines(const BatchDev &B, double *d_signal, const double *d_knots, const double *d_coefs,
+                        const int64_t *d_spl_off, int degree, int64_t total, cudaStream_t st) {
+  if (total > 0)
+    apply_splines_kernel<<<blocks_for(total), 256, 0, st>>>(B, d_signal, d_knots, d_coefs, d_spl_off, degree, total);
 }
 
 void nvbk_chunk_values(const BatchDev &B, const double *d_ll, const int32_t *d_reverse, double nel, int64_t total,

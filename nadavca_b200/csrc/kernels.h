@@ -35,6 +35,8 @@ void nvbk_alignment_table(const BatchDev &B, const int32_t *d_events, const int3
                           const int32_t *d_reverse, int64_t total, int64_t *d_out, cudaStream_t st);
 void nvbk_event_means(const BatchDev &B, const int32_t *d_events, const int32_t *d_status, int64_t total, double *d_out,
                       cudaStream_t st);
+void nvbk_apply_splines(const BatchDev &B, double *d_signal, const double *d_knots, const double *d_coefs,
+                        const int64_t *d_spl_off, int degree, int64_t total, cudaStream_t st);
 void nvbk_chunk_values(const BatchDev &B, const double *d_ll, const int32_t *d_reverse, double nel, int64_t total,
                        double *d_chunks, cudaStream_t st);
 void nvbk_scatter_add(const BatchDev &B, const double *d_chunks, const int64_t *d_dest, const int32_t *d_status,

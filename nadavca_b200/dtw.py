@@ -148,6 +148,34 @@ class Batch:
         _cabi.check(self.lib.nvb_batch_set_signal(self.handle, _cabi.ptr(flat, ctypes.c_double)),
                     'nvb_batch_set_signal')
 
+    def apply_splines(self, splines, stream=None):
+        """Replace every read's resident signal x by spline(x); `splines` holds one FITPACK (t, c, k) tuple per read
+        as returned by scipy.interpolate.splrep, or None to leave that read untouched."""
+        degree = next((int(s[2]) for s in splines if s is not None), 3)
+        off = np.zeros(self.n_reads + 1, dtype=np.int64)
+        knots, coefs = [], []
+        for i, s in enumerate(splines):
+            n = 0
+            if s is not None:
+                if int(s[2]) != degree:
+                    raise ValueError('all splines of a batch must have the same degree')
+                n = len(s[0])
+                knots.append(np.asarray(s[0], dtype=np.float64))
+                coefs.append(np.asarray(s[1], dtype=np.float64)[:n])
+            off[i + 1] = off[i] + n
+        t = np.ascontiguousarray(np.concatenate(knots) if knots else np.zeros(0))
+        c = np.ascontiguousarray(np.concatenate(coefs) if coefs else np.zeros(0))
+        _cabi.check(self.lib.nvb_batch_apply_splines(self.handle, _cabi.ptr(t, ctypes.c_double),
+                                                     _cabi.ptr(c, ctypes.c_double), _cabi.ptr(off, ctypes.c_int64),
+                                                     degree, _stream(stream)), 'nvb_batch_apply_splines')
+
+    def signals(self):
+        """The resident signal values per read (after set_signals / apply_splines)."""
+        out = np.zeros(self.pack.total_signal, dtype=np.float64)
+        _cabi.check(self.lib.nvb_batch_get_signal(self.handle, _cabi.ptr(out, ctypes.c_double)), 'nvb_batch_get_signal')
+        off = self.pack.signal_off
+        return [out[off[i]:off[i + 1]] for i in range(self.n_reads)]
+
     # -- kernels ----------------------------------------------------------------------------------------------
     def refine(self, model_transitions, stream=None):
         _cabi.check(self.lib.nvb_batch_refine(self.handle, int(bool(model_transitions)), _stream(stream)),

@@ -207,10 +207,11 @@ class ProbabilityEstimator:
                     return [], None
                 signals = [signals[i] for i in keep]
                 batch = self._batch(items, signals)
-            for it, ev, exp_sig, means in zip(items, events, expected, event_means):
-                it.read.tweak_signal_normalization(ev.astype(int) + it.signal_range[0], exp_sig, means.tolist())
-            batch.set_signals([it.read.tweaked_normalized_signal[it.signal_range[0]:it.signal_range[1]]
-                               for it in items])
+            # host: the smoothing-spline FIT per read (scipy splrep, read.py:93); device: its EVALUATION over the
+            # resident signal slices (read.py:94), which therefore never travel back to the host
+            splines = [it.read.fit_tweak_spline(ev.astype(int) + it.signal_range[0], exp_sig, means)
+                       for it, ev, exp_sig, means in zip(items, events, expected, event_means)]
+            batch.apply_splines(splines)
         batch.estimate(self.model_wobbling)
         return items, batch
 

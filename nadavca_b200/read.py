@@ -12,11 +12,25 @@ class Read:
     def __init__(self):
         self.raw_signal = None
         self.normalized_signal = None
-        self.tweaked_normalized_signal = None
+        self._tweaked_normalized_signal = None
+        self.tweak_spline = None
         self.strand = None
         self.fastq = None
         self.sequence_to_signal_mapping = None
         self.sequence = None
+
+    @property
+    def tweaked_normalized_signal(self):
+        """read.py:94.  The batched estimator evaluates the tweak spline on the GPU for the aligned slice only and
+        keeps the spline (``tweak_spline``); the whole-read array of the reference is produced on first access with
+        the same scipy call."""
+        if self._tweaked_normalized_signal is None and self.tweak_spline is not None:
+            self._tweaked_normalized_signal = interpolate.splev(self.normalized_signal, self.tweak_spline)
+        return self._tweaked_normalized_signal
+
+    @tweaked_normalized_signal.setter
+    def tweaked_normalized_signal(self, value):
+        self._tweaked_normalized_signal = value
 
     @staticmethod
     def from_arrays(raw_signal, sequence, sequence_to_signal_mapping, name='read'):
@@ -52,14 +66,22 @@ class Read:
         `event_means` (optional) are the per-event means of ``normalized_signal`` already computed on the device by
         ``dtw.Batch.event_means`` -- bit-identical to the ``numpy.mean`` calls of the reference's per-event Python
         loop, which at ~2000 events per read is the dominant host cost of ``estimate_snps``."""
+        spline = self.fit_tweak_spline(alignment, expected_means, event_means)
+        self.tweaked_normalized_signal = interpolate.splev(self.normalized_signal, spline)
+
+    def fit_tweak_spline(self, alignment, expected_means, event_means=None):
+        """The spline of ``tweak_signal_normalization`` (read.py:84-93) as FITPACK's (knots, coefficients, degree);
+        also kept in ``self.tweak_spline``.  Pairs farther than 1 from their expected level are dropped, the rest is
+        sorted by (mean, expected) like the reference's list of tuples."""
         if event_means is None:
             event_means = [numpy.mean(self.normalized_signal[event[0]: event[1]]) for event in alignment]
-        data = []
-        for mean, expected_mean in zip(event_means, expected_means):
-            if abs(expected_mean - mean) <= 1:
-                data.append((mean, expected_mean))
-        data.sort()
-        means = [d[0] for d in data]
-        expected = [d[1] for d in data]
-        spline = interpolate.splrep(means, expected, s=len(means))
-        self.tweaked_normalized_signal = interpolate.splev(self.normalized_signal, spline)
+        means = numpy.asarray(event_means, dtype=float)
+        expected = numpy.asarray(expected_means, dtype=float)
+        with numpy.errstate(invalid='ignore'):
+            keep = numpy.abs(expected - means) <= 1  # a NaN mean (empty event) fails the test, as in the reference
+        means, expected = means[keep], expected[keep]
+        order = numpy.lexsort((expected, means))
+        means, expected = means[order], expected[order]
+        self.tweak_spline = interpolate.splrep(means, expected, s=len(means))
+        self._tweaked_normalized_signal = None
+        return self.tweak_spline

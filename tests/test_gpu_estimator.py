@@ -258,3 +258,37 @@ def test_event_means_equal_numpy_mean_bit_for_bit(golden_estimator, default_mode
 def make_case_local(rng, k, cp, n, bw, mel, spacing):
     from conftest import make_case
     return make_case(rng, k, cp, n, bw, mel, spacing=spacing)[2:]
+
+
+def test_device_spline_evaluation_matches_scipy(golden_estimator, default_model):
+    """nvb_batch_apply_splines == scipy.interpolate.splev (FITPACK) on the splines the tweak fits, including
+    extrapolation beyond the knots and reads left untouched."""
+    from scipy import interpolate
+    from nadavca_b200 import dtw, synthetic
+    from nadavca_b200.genome import Genome
+    from nadavca_b200.read import Read
+    g = golden_estimator
+    genome = g['genome']
+    reads = golden_reads(g)
+    Read.normalize_reads(reads)
+    aligner = synthetic.SyntheticAligner(genome)
+    km = default_model
+    args, splines = [], []
+    for i, r in enumerate(reads):
+        apx = aligner.get_signal_alignment(r, 30)
+        s0, s1 = apx.signal_range
+        a, b = apx.read_sequence_range
+        ref = Genome.to_numerical(apx.reference_part)
+        cb, ca = Genome.to_numerical(r.sequence[a - 2:a]), Genome.to_numerical(r.sequence[b:b + 3])
+        args.append((r.normalized_signal[s0:s1], ref, cb, ca, apx.alignment))
+        table = g['tweak1/read%d/alignment_table' % i]
+        expected = km.get_expected_signal(ref, cb, ca)
+        splines.append(None if i == 3 else r.fit_tweak_spline(table[:, 1:], expected))
+    with dtw.Batch(km, *[list(x) for x in zip(*args)], 30, 2) as batch:
+        batch.apply_splines(splines)
+        got = batch.signals()
+    for sig, spl, a in zip(got, splines, args):
+        want = a[0] if spl is None else interpolate.splev(a[0], spl)
+        if spl is not None:  # some samples lie outside the knot range: the extrapolation branch is exercised
+            assert a[0].min() < spl[0][0] or a[0].max() > spl[0][-1]
+        np.testing.assert_allclose(sig, want, rtol=1e-13, atol=1e-13)
