@@ -440,13 +440,16 @@ def run_ours(args):
         t, a = pinned(getattr(pk, name))
         keep.append(t)
         host[name] = a
-    tw_t, tw_flat = pinned(np.concatenate(tweaked))
+    # the tweak splines were fitted on the host during the (untimed) preparation; the product path evaluates them on
+    # the device (estimator._run_estimate), so the end-to-end step uploads knots and coefficients, not signals
+    splines = [it['read'].tweak_spline for it in items]
+    spline_bytes = sum(2 * 8 * len(sp[0]) for sp in splines) + 8 * (len(splines) + 1)
     pack = _cabi.ReadsPack.from_packed(bandwidth=args.bandwidth, min_event_length=mel, **host)
-    h2d = sum(a.nbytes for a in host.values()) + tw_flat.nbytes
+    h2d = sum(a.nbytes for a in host.values()) + spline_bytes
     ev_host = torch.empty((pk.total_reference, 2), dtype=torch.int32).pin_memory()
     st_host = torch.empty(pk.n_reads, dtype=torch.int32).pin_memory()
     prob_host = torch.empty((pk.total_reference, 4), dtype=torch.float64).pin_memory()
-    d2h = ev_host.numel() * 4 + st_host.numel() * 4 + prob_host.numel() * 8
+    d2h = ev_host.numel() * 4 + st_host.numel() * 4 + prob_host.numel() * 8 + pk.total_reference * 8
     import ctypes
     lib = _cabi.load()
 
@@ -455,7 +458,8 @@ def run_ours(args):
         b.refine(False, stream)
         _cabi.check(lib.nvb_batch_get_events(b.handle, ctypes.cast(ev_host.data_ptr(), _cabi.c_i32p),
                                              ctypes.cast(st_host.data_ptr(), _cabi.c_i32p)), 'get_events')  # D2H
-        b.set_signals(tw_flat)                                   # H2D of the tweaked signals
+        b.event_means()                                          # D2H of the per-event means (input of the fit)
+        b.apply_splines(splines, stream)                         # H2D of the splines, evaluation on the device
         b.estimate(True, stream)
         res = est.posterior_stage(b, reverse, intervals, genome, independent=True, plan=plan)
         prob_host.copy_(res[2], non_blocking=True)               # D2H of the step's result
