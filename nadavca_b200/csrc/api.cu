@@ -374,14 +374,28 @@ int plan_waves(nvb_batch *b, int mode, bool need_dp, std::vector<Wave> &waves, s
                std::vector<int64_t> &dp_base, std::vector<int64_t> &rec_base, int64_t &max_cells, int64_t &max_dp,
                int64_t &max_rec) {
   int64_t limit = b->ws_limit;
-  if (limit <= 0) {
-    size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
-    // memory already held by this batch's workspace can be reused
-    free_b += b->model->ws.bytes();
-    limit = (int64_t)(free_b * 0.7);
-  }
   const int n = b->n_reads;
+  if (limit <= 0) {
+    // When the whole batch fits the workspace the model already owns, nothing has to be asked of the driver
+    // (cudaMemGetInfo costs milliseconds); otherwise plan against 70 % of what is free plus what is already held.
+    int64_t cells = 0, dp = 0, rec = 0;
+    for (int j = 0; j < n; j++) {
+      cells += matrix_cells(b, j, mode);
+      if (need_dp) { dp += 2 * (int64_t)b->maxw[j]; rec += record_words(b, j, mode); }
+    }
+    const Workspace &ws = b->model->ws;
+    const bool fits = (size_t)cells * sizeof(double) <= ws.pF.capacity && (size_t)cells * sizeof(double) <= ws.sF.capacity &&
+                      (size_t)cells * sizeof(int32_t) <= ws.pX.capacity && (size_t)cells * sizeof(int32_t) <= ws.sX.capacity &&
+                      (size_t)dp * sizeof(double) <= ws.dp.capacity && (size_t)rec * sizeof(uint32_t) <= ws.records.capacity;
+    if (fits) {
+      limit = INT64_MAX;
+    } else {
+      size_t free_b = 0, total_b = 0;
+      CU(cudaMemGetInfo(&free_b, &total_b));
+      free_b += ws.bytes();
+      limit = (int64_t)(free_b * 0.7);
+    }
+  }
   mat_base.assign(n, 0); dp_base.assign(n, 0); rec_base.assign(n, 0);
   waves.clear();
   max_cells = 0; max_dp = 0; max_rec = 0;

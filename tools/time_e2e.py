@@ -23,7 +23,9 @@ keep, host = [], {}
 for name in ('signal', 'signal_off', 'reference', 'reference_off', 'context_before', 'context_before_off',
              'context_after', 'context_after_off', 'anchors', 'anchor_off'):
     t, a = pinned(getattr(pk, name)); keep.append(t); host[name] = a
-tw_t, tw_flat = pinned(pk.signal.copy())
+from scipy import interpolate
+xs = np.linspace(-4, 4, 40)
+splines = [interpolate.splrep(xs, xs + 0.01 * np.sin(xs), s=40) for _ in range(pk.n_reads)]
 pack = _cabi.ReadsPack.from_packed(bandwidth=150, min_event_length=2, **host)
 ev_host = torch.empty((pk.total_reference, 2), dtype=torch.int32).pin_memory()
 st_host = torch.empty(pk.n_reads, dtype=torch.int32).pin_memory()
@@ -35,10 +37,11 @@ for it in range(4):
     b = dtw.Batch.from_pack(km, pack); t.append(time.perf_counter())
     b.refine(False, stream); t.append(time.perf_counter())
     _cabi.check(lib.nvb_batch_get_events(b.handle, ctypes.cast(ev_host.data_ptr(), _cabi.c_i32p), ctypes.cast(st_host.data_ptr(), _cabi.c_i32p)), 'ev'); t.append(time.perf_counter())
-    b.set_signals(tw_flat); t.append(time.perf_counter())
+    b.event_means(); t.append(time.perf_counter())
+    b.apply_splines(splines, stream); t.append(time.perf_counter())
     b.estimate(True, stream); t.append(time.perf_counter())
     res = est.posterior_stage(b, reverse, intervals, genome, independent=True, plan=plan); t.append(time.perf_counter())
     prob_host.copy_(res[2], non_blocking=True); torch.cuda.synchronize(); t.append(time.perf_counter())
     b.close(); t.append(time.perf_counter())
     d = np.diff(t) * 1e3
-    print('create %.1f | refine %.1f | get_events %.1f | set_signals %.1f | estimate %.1f | posterior %.1f | d2h+sync %.1f | close %.1f | total %.1f' % (tuple(d) + (d.sum(),)))
+    print('create %.1f | refine %.1f | get_events %.1f | event_means %.1f | apply_splines %.1f | estimate %.1f | posterior %.1f | d2h+sync %.1f | close %.1f | total %.1f' % (tuple(d) + (d.sum(),)))
