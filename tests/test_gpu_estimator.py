@@ -292,3 +292,36 @@ def test_device_spline_evaluation_matches_scipy(golden_estimator, default_model)
         if spl is not None:  # some samples lie outside the knot range: the extrapolation branch is exercised
             assert a[0].min() < spl[0][0] or a[0].max() > spl[0][-1]
         np.testing.assert_allclose(sig, want, rtol=1e-13, atol=1e-13)
+
+
+def test_full_size_batch_alignments_bit_exact(default_model):
+    """32 reads of the BASELINE size (~2000 bases, ~20k samples, bandwidth 150, both strands) through both alignment
+    modes: every event boundary equals the oracle's; split into waves by a small workspace limit on the way."""
+    from nadavca_b200 import dtw, synthetic
+    from nadavca_b200.genome import Genome
+    from nadavca_b200.read import Read
+    from oracle import oracle as orc
+    km = default_model
+    genome = synthetic.make_genome(200_000, seed=12)
+    reads = [synthetic.make_read(genome, km, 5000 + i) for i in range(32)]
+    Read.normalize_reads(reads)
+    aligner = synthetic.SyntheticAligner(genome)
+    args = []
+    for r in reads:
+        apx = aligner.get_signal_alignment(r, 150)
+        s0, s1 = apx.signal_range
+        a, b = apx.read_sequence_range
+        args.append((r.normalized_signal[s0:s1], Genome.to_numerical(apx.reference_part),
+                     Genome.to_numerical(r.sequence[a - 2:a]), Genome.to_numerical(r.sequence[b:b + 3]),
+                     apx.alignment))
+    om = orc.OracleModel(6, 2, 4, km.mean, km.sigma, 'port')
+    total = 0
+    with dtw.Batch(km, *[list(x) for x in zip(*args)], 150, 2, workspace_limit=400_000_000) as batch:
+        for flag in (False, True):
+            batch.refine(flag)
+            events, status = batch.events()
+            assert np.all(status == 0)
+            for ev, a in zip(events, args):
+                assert ev.tolist() == orc.refine_alignment(*a, 150, 2, om, flag)
+                total += len(ev)
+    assert total > 2 * 32 * 1500
