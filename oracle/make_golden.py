@@ -13,7 +13,8 @@ outputs of the reference itself, run in the build container:
                            imported under the four shims of SURVEY.md 8c) on top of that module:
                            ProbabilityEstimator.get_refined_alignment, ._estimate_log_likelihoods and
                            .estimate_probabilities on seeded synthetic reads (both strands, overlapping and disjoint
-                           chunks, with and without the spline tweak).  The reads themselves (raw signal, sequence,
+                           chunks, with and without the spline tweak) and calculate_meth_scores of
+                           nadavca/detect_meth.py on those alignments.  The reads themselves (raw signal, sequence,
                            base->sample map, truth) are stored so that the tests do not depend on the generator.
 
 Needs /root/reference (absent on the GPU box): run here with  `python oracle/make_golden.py`  and commit the .npz.
@@ -153,6 +154,17 @@ def make_estimator_cases():
             out[pre + 'read%d/chunk_values' % i] = np.asarray(chunk.values, dtype=np.float64)
             ind = est.estimate_probabilities(genome, [rr])[0]
             out[pre + 'read%d/independent_probabilities' % i] = np.asarray(ind.values, dtype=np.float64)
+        if tweak:
+            # nadavca/detect_meth.py:26-55 on the reference's own refined alignments (pattern "CG")
+            import nadavca.detect_meth as ref_meth
+            for i, rr in enumerate(ref_reads):
+                apx, table = est.get_refined_alignment(rr)
+                cut = rr.normalized_signal[table[0][1]:table[-1][2]]
+                feats = ref_meth.calculate_meth_scores(cut, table, apx, 'CG', ref_model)
+                out['meth/read%d/positions' % i] = np.array([f[0] for f in feats], dtype=np.int64)
+                out['meth/read%d/contexts' % i] = np.array([f[1] for f in feats], dtype='U11')
+                out['meth/read%d/scores' % i] = np.array([f[2] for f in feats], dtype=np.float64).reshape(-1, 11)
+                out['meth/read%d/aggregated' % i] = np.array([ref_meth.maxs3(f[2]) for f in feats], dtype=np.float64)
         groups = est.estimate_probabilities(genome, ref_reads)
         out[pre + 'n_groups'] = np.array(len(groups))
         for g, chunk in enumerate(groups):

@@ -325,3 +325,33 @@ def test_full_size_batch_alignments_bit_exact(default_model):
                 assert ev.tolist() == orc.refine_alignment(*a, 150, 2, om, flag)
                 total += len(ev)
     assert total > 2 * 32 * 1500
+
+
+def test_detect_meth_api(golden_estimator, default_model, tmp_path):
+    """detect_meth end to end on the GPU path: CSV layout of the reference, scores consistent with the returned
+    alignments and the renormalised signals."""
+    import csv
+    import nadavca_b200
+    from nadavca_b200 import synthetic
+    from nadavca_b200.detect_meth import calculate_meth_scores, maxs3
+    g = golden_estimator
+    genome = g['genome']
+    aligner = synthetic.SyntheticAligner(genome)
+    reads = golden_reads(g)
+    out = tmp_path / 'meth.csv'
+    rows = nadavca_b200.detect_meth(None, reads, 'CG', str(out), config=GOLDEN_CONFIG, kmer_model=default_model,
+                                    aligner=aligner, reference=genome, names=['r%d' % i for i in range(len(reads))])
+    with open(out) as fh:
+        lines = list(csv.reader(fh))
+    assert lines[0] == ['Filename', 'Position', 'Sequence context', 'Position scores', 'Aggregated score']
+    assert len(lines) == len(rows) + 1 and len(rows) >= 10
+    # recompute from an independent align_signal run over fresh copies of the reads
+    again = list(nadavca_b200.align_signal(None, golden_reads(g), config=GOLDEN_CONFIG, kmer_model=default_model,
+                                           aligner=aligner, reference=genome))
+    want = []
+    for i, (read, (apx, alignment)) in enumerate(again):
+        cut = read.normalized_signal[alignment[0][1]:alignment[-1][2]]
+        for pos, context, scores in calculate_meth_scores(cut, alignment, apx, 'CG', default_model):
+            assert len(context) == 11 and context[5:7] == 'CG' and len(scores) == 11
+            want.append(('r%d' % i, pos, context, ','.join(map(str, scores)), maxs3(scores)))
+    assert rows == want

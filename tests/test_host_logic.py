@@ -218,3 +218,31 @@ def test_tweak_with_precomputed_event_means(golden_estimator):
     means = [float(np.mean(r.normalized_signal[s:e])) for s, e in events]
     r.tweak_signal_normalization(events, expected, means)
     assert np.array_equal(a, r.tweaked_normalized_signal)
+
+
+def test_meth_scores_match_reference_golden(golden_estimator, default_model_host):
+    """calculate_meth_scores / maxs3 == nadavca/detect_meth.py:26-60 on the reference's own refined alignments
+    (golden, pattern "CG"); the expected levels come from the oracle model so the test needs no GPU."""
+    from nadavca_b200 import synthetic
+    from nadavca_b200.detect_meth import calculate_meth_scores, maxs3
+    from nadavca_b200.read import Read
+    from oracle import oracle as orc
+    g = golden_estimator
+    km = default_model_host
+    om = orc.OracleModel(km.get_k(), km.get_central_position(), 4, km.mean, km.sigma, 'port')
+    reads = golden_reads(g)
+    Read.normalize_reads(reads)
+    aligner = synthetic.SyntheticAligner(g['genome'])
+    total = 0
+    for i, r in enumerate(reads):
+        table = g['tweak1/read%d/alignment_table' % i]
+        apx = aligner.get_signal_alignment(r, 30)
+        cut = r.normalized_signal[table[0][1]:table[-1][2]]
+        feats = calculate_meth_scores(cut, table, apx, 'CG', om)
+        assert [f[0] for f in feats] == g['meth/read%d/positions' % i].tolist()
+        assert [f[1] for f in feats] == g['meth/read%d/contexts' % i].tolist()
+        got = np.array([f[2] for f in feats]).reshape(-1, 11)
+        assert np.array_equal(got, g['meth/read%d/scores' % i])
+        assert [maxs3(f[2]) for f in feats] == g['meth/read%d/aggregated' % i].tolist()
+        total += len(feats)
+    assert total >= 10
