@@ -560,8 +560,21 @@ def cpu_baseline(km, items, tweaked, args, mel):
             'sample': 'first %d reads of the workload, one per worker process, %.1f s wall' % (n_sample, t)}
 
 
+def relaunch_under_torchrun(args):
+    """`python bench.py --gpus N` (N > 1) without a launcher: start one rank per GPU on this node ourselves."""
+    import socket
+    with socket.socket() as sock:
+        sock.bind(('127.0.0.1', 0))
+        port = sock.getsockname()[1]
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
+           '--master-addr', '127.0.0.1', '--master-port', str(port), os.path.abspath(__file__)] + sys.argv[1:]
+    raise SystemExit(subprocess.call(cmd))
+
+
 if __name__ == '__main__':
     a = parse_args()
+    if a.gpus > 1 and 'WORLD_SIZE' not in os.environ:
+        relaunch_under_torchrun(a)
     if a.impl == 'reference':
         run_reference(a)
     else:
