@@ -48,6 +48,7 @@ def estimate_snps(reference_filename,
     for i, read in enumerate(reads):
         if isinstance(read, str):
             reads[i] = Read.load_from_fast5(read, group_name)
-    Read.normalize_reads(reads)  # ONE median/MAD pooled over all reads (estimate_snps.py:61)
+    # ONE median/MAD pooled over all reads (estimate_snps.py:61) -- over the reads of all ranks in a sharded job
+    Read.normalize_reads(reads, process_group)
     return estimator.estimate_probabilities(reference, reads, independent=independent,
                                             process_group=process_group)

@@ -120,3 +120,37 @@ def test_bench_rank_helpers_gloo(tmp_path):
     mp.spawn(_bench_rank_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     firsts = [int(np.load(os.path.join(str(tmp_path), 'first%d.npy' % r))[0]) for r in range(world)]
     assert firsts == [0, 5]
+
+
+def _median_worker(rank, world, port, result_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from nadavca_b200.read import Read, distributed_median
+        rng = np.random.default_rng(99)
+        results = []
+        for n_total in (7, 10, 1, 2001, 4000):
+            pooled = np.round(rng.normal(90, 15, size=n_total) * (4 if n_total > 100 else 1)) / 4.0  # with ties
+            pooled[::3] *= -1
+            mine = pooled[rank::world]
+            results.append((distributed_median(mine, dist.group.WORLD), float(np.median(pooled))))
+        # Read.normalize_reads over shards == over the pooled reads
+        raws = [rng.normal(90, 15, size=int(rng.integers(50, 200))) for _ in range(9)]
+        reads = [Read.from_arrays(r, 'ACGT', {0: 0}) for r in raws]
+        Read.normalize_reads(reads[rank::world], dist.group.WORLD)
+        pooled_reads = [Read.from_arrays(r, 'ACGT', {0: 0}) for r in raws]
+        Read.normalize_reads(pooled_reads)
+        same = all(np.array_equal(a.normalized_signal, b.normalized_signal)
+                   for a, b in zip(reads[rank::world], pooled_reads[rank::world]))
+        np.save(os.path.join(result_dir, 'median%d.npy' % rank), np.array(results + [(float(same), 1.0)]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_distributed_median_is_exact_gloo(tmp_path):
+    world = 2
+    mp.spawn(_median_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        res = np.load(os.path.join(str(tmp_path), 'median%d.npy' % r))
+        assert np.array_equal(res[:, 0], res[:, 1]), res

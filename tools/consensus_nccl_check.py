@@ -20,23 +20,24 @@ dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 km = KmerModel.load_from_hdf5(os.path.join(ROOT, 'nadavca_b200', 'default', 'kmer_model.hdf5'))
 cfg = dict(bandwidth=150, snp_prior_probability=0.001, min_event_length=2, model_wobbling=True, model_transitions=True,
            tweak_signal_normalization=True, normalization_event_length=10)
-n_reads, G = int(sys.argv[1]) if len(sys.argv) > 1 else 64, 30_000
+n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+G = int(sys.argv[2]) if len(sys.argv) > 2 else 30_000
+n_bases = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
 genome = synthetic.make_genome(G, seed=5)
-make = lambda: [synthetic.make_read(genome, km, 2000 + i, n_bases=1000) for i in range(n_reads)]
+make = lambda: [synthetic.make_read(genome, km, 2000 + i, n_bases=n_bases) for i in range(n_reads)]
 aligner = synthetic.SyntheticAligner(genome)
 reads = make()
-# estimate_snps pools the normalisation over the reads it is given (estimate_snps.py:61): normalise ALL reads once
-# here and hand the already normalised shard to the estimator, as a multi-GPU driver of the reference would
-nadavca_b200.Read.normalize_reads(reads)
 work = [len(r.raw_signal) for r in reads]
 mine = shard_reads(work, world)[rank]
-est = nadavca_b200.estimator.ProbabilityEstimator(km, aligner, cfg)
+# the public API on this rank's shard: pooled normalisation over the reads of ALL ranks (exact distributed median),
+# refine -> tweak -> SNP DP on the local shard, one NCCL all-reduce of the per-position sums, posterior
 torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
-chunks = est.estimate_probabilities(genome, [reads[i] for i in mine], independent=False, process_group=dist.group.WORLD)
+chunks = nadavca_b200.estimate_snps(None, [reads[i] for i in mine], reference=genome, config=cfg, kmer_model=km,
+                                    independent=False, aligner=aligner, process_group=dist.group.WORLD)
 torch.cuda.synchronize(); dist.barrier(); t1 = time.perf_counter()
 if rank == 0:
-    reads1 = make(); nadavca_b200.Read.normalize_reads(reads1)
-    single = nadavca_b200.estimator.ProbabilityEstimator(km, aligner, cfg).estimate_probabilities(genome, reads1, independent=False)
+    single = nadavca_b200.estimate_snps(None, make(), reference=genome, config=cfg, kmer_model=km, independent=False,
+                                        aligner=aligner)
     assert [(c.start, c.end) for c in chunks] == [(c.start, c.end) for c in single]
     worst = 0.0
     for a, b in zip(chunks, single):
