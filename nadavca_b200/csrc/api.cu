@@ -131,6 +131,7 @@ struct Workspace {
 
 struct nvb_model {
   int device = 0;
+  int sm_count = 148;
   ModelDev dev{};
   DevBuf<double> mean, ac, mc;
   Workspace ws;
@@ -151,7 +152,7 @@ struct nvb_batch {
   DevBuf<int32_t> d_bs, d_be, d_flags, d_maxw;
   DevBuf<int64_t> d_cell_off, d_summary;
   std::vector<int64_t> cells, w0, wn;  // per read: sum of widths over n+1 band rows, first / last width
-  std::vector<int32_t> maxw, flags;
+  std::vector<int32_t> maxw, flags, no_rotation;  // no_rotation: the read needs the striped sweep (rows4.cu)
   // results
   DevBuf<int32_t> d_events, d_status;
   DevBuf<double> d_ll;
@@ -225,6 +226,10 @@ nvb_model *nvb_model_create(int k, int central_position, int alphabet_size, cons
   if (cudaSetDevice(device) != cudaSuccess) { fail(NVB_ECUDA, "cudaSetDevice(%d) failed", device); return nullptr; }
   nvb_model *m = new nvb_model();
   m->device = device;
+  {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) m->sm_count = sms;
+  }
   std::vector<double> ac(n_kmers), mc(n_kmers);
   for (int64_t i = 0; i < n_kmers; i++) {  // same expressions as kmer_model.cpp:10-13, host libm
     double s = sigma[i];
@@ -341,15 +346,35 @@ int batch_init(nvb_batch *b, const nvb_reads *r) {
   std::vector<int64_t> summary((size_t)4 * n);
   CU(cudaMemcpyAsync(summary.data(), b->d_summary.p, summary.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  b->cells.resize(n); b->w0.resize(n); b->wn.resize(n); b->maxw.resize(n); b->flags.resize(n);
+  b->cells.resize(n); b->w0.resize(n); b->wn.resize(n); b->maxw.resize(n); b->flags.resize(n); b->no_rotation.resize(n);
   for (int i = 0; i < n; i++) {
     b->cells[i] = summary[4 * i];
     b->w0[i] = summary[4 * i + 1];
     b->wn[i] = summary[4 * i + 2];
     b->maxw[i] = (int32_t)(summary[4 * i + 3] & 0xffffffffLL);
-    b->flags[i] = (summary[4 * i + 3] >> 32) ? NVB_READ_BAD_BAND : 0;
+    b->flags[i] = ((summary[4 * i + 3] >> 32) & 1) ? NVB_READ_BAD_BAND : 0;
+    b->no_rotation[i] = (int32_t)((summary[4 * i + 3] >> 33) & 1);
   }
   return NVB_OK;
+}
+
+// Forward + backward rows of one wave: the rotating wavefront (rows5.cu) when every read of the wave allows it, else
+// the pipelined stripes (rows4.cu).
+int run_sweep(nvb_batch *b, int mode, const Wave &w, cudaStream_t st) {
+  const ModelDev &M = b->model->dev;
+  Workspace &ws = b->model->ws;
+  // Measured on B200 (profiles/r01d_sweep_schedules.txt): the rotating wavefront needs half the warp-steps but ~1.4x
+  // the instructions per step and one warp per direction instead of two.  It wins when its warps (2 per read) fill one
+  // resident wave of the GPU (16 warps per SM at its 128 registers) to 60 % or more; with fewer reads the striped
+  // sweep hides latency better, with more the second wave eats the gain.
+  const int items = 2 * (w.b1 - w.b0);
+  const int resident = b->model->sm_count * 16;
+  bool rotate = w.maxw <= 640 && 10 * items >= 6 * resident && items <= resident;
+  if (const char *env = getenv("NVB_SWEEP")) rotate = w.maxw <= 640 && env[0] == 'r';  // experiments: r / s
+  for (int i = w.b0; i < w.b1 && rotate; i++) rotate = !b->no_rotation[i];
+  if (rotate)
+    return nvbk_sweep_rotate(M, b->dev, mode, w.b0, w.b1, b->d_mat_base.p, ws.pF.p, ws.pX.p, ws.sF.p, ws.sX.p, st);
+  return nvbk_sweep2(M, b->dev, mode, w.b0, w.b1, w.maxw, b->d_mat_base.p, ws.pF.p, ws.pX.p, ws.sF.p, ws.sX.p, st);
 }
 
 int64_t matrix_cells(const nvb_batch *b, int i, int mode) {
@@ -511,8 +536,7 @@ int nvb_batch_refine(nvb_batch *b, int model_transitions, void *stream) {
   for (const Wave &w : waves) {
     {
       StageTimer t(b, 0, st);
-      const int src = nvbk_sweep2(b->model->dev, b->dev, mode, w.b0, w.b1, w.maxw, b->d_mat_base.p, b->model->ws.pF.p,
-                                  b->model->ws.pX.p, b->model->ws.sF.p, b->model->ws.sX.p, st);
+      const int src = run_sweep(b, mode, w, st);
       if (src == -1) return fail(NVB_EINVAL, "min_event_length %d is not supported (maximum 6)", b->dev.mel);
       if (src) return fail(NVB_ENOMEM, "band row of %d columns does not fit the sweep's shared-memory hand-off rows", w.maxw);
     }
@@ -547,8 +571,7 @@ int nvb_batch_estimate(nvb_batch *b, int model_wobbling, void *stream) {
   for (const Wave &w : waves) {
     {
       StageTimer t(b, 0, st);
-      const int src = nvbk_sweep2(M, b->dev, mode, w.b0, w.b1, w.maxw, b->d_mat_base.p, b->model->ws.pF.p, b->model->ws.pX.p,
-                                  b->model->ws.sF.p, b->model->ws.sX.p, st);
+      const int src = run_sweep(b, mode, w, st);
       if (src == -1) return fail(NVB_EINVAL, "min_event_length %d is not supported (maximum 6)", b->dev.mel);
       if (src) return fail(NVB_ENOMEM, "band row of %d columns does not fit the sweep's shared-memory hand-off rows", w.maxw);
     }

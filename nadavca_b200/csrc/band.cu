@@ -25,8 +25,8 @@ __global__ void __launch_bounds__(kThreads) band_kernel(BatchDev B, int64_t *sum
   const int bw = B.bandwidth;
 
   __shared__ long long s_part[kThreads];
-  __shared__ int s_bad, s_maxw;
-  if (tid == 0) { s_bad = 0; s_maxw = 0; }
+  __shared__ int s_bad, s_maxw, s_overlap;
+  if (tid == 0) { s_bad = 0; s_maxw = 0; s_overlap = -0x7fffffff; }
 
   for (int j = tid; j < rows; j += kThreads) { bs[j] = 0; be[j] = N; coff[j] = -1; }
   __syncthreads();
@@ -78,6 +78,12 @@ __global__ void __launch_bounds__(kThreads) band_kernel(BatchDev B, int64_t *sum
     sum += w;
     maxw = max(maxw, w);
   }
+  // rotating sweep (rows5.cu): a lane's slot must be free again two generations (64 pairs) later, i.e. band row j must
+  // end at most 48 columns beyond the start of band row j + 63
+  int overlap = -0x7fffffff;
+  for (int j = lo; j < hi; j++)
+    if (j + 63 < rows) overlap = max(overlap, be[j] - bs[j + 63]);
+  atomicMax(&s_overlap, overlap);
   s_part[tid] = sum;
   if (bad) atomicOr(&s_bad, 1);
   atomicMax(&s_maxw, maxw);
@@ -100,7 +106,8 @@ __global__ void __launch_bounds__(kThreads) band_kernel(BatchDev B, int64_t *sum
     summary[4 * b + 0] = total;
     summary[4 * b + 1] = rows > 0 ? max(0, be[0] - bs[0] + 1) : 0;
     summary[4 * b + 2] = rows > 0 ? max(0, be[n] - bs[n] + 1) : 0;
-    summary[4 * b + 3] = ((long long)(bad_all ? 1 : 0) << 32) | (unsigned)s_maxw;
+    const int no_rotation = s_overlap > 48;
+    summary[4 * b + 3] = ((long long)(bad_all ? 1 : 0) << 32) | ((long long)no_rotation << 33) | (unsigned)s_maxw;
   }
 }
 

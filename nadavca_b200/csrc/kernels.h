@@ -11,6 +11,10 @@ void nvbk_expected_signal(const ModelDev &M, const BatchDev &B, int64_t total, d
 // row of the wave.  Returns -1 for an unsupported min_event_length, -2 when the hand-off rows do not fit shared memory.
 int nvbk_sweep2(const ModelDev &M, const BatchDev &B, int mode, int b0, int b1, int wave_maxw,
                 const int64_t *d_mat_base, double *pF, int32_t *pX, double *sF, int32_t *sX, cudaStream_t st);
+// rows5.cu: the same rows with one continuously rotating wavefront per (read, direction); for reads whose bands allow
+// it (band.cu flags the others).  Returns -1 for an unsupported min_event_length.
+int nvbk_sweep_rotate(const ModelDev &M, const BatchDev &B, int mode, int b0, int b1, const int64_t *d_mat_base,
+                      double *pF, int32_t *pX, double *sF, int32_t *sX, cudaStream_t st);
 // no-SNP total (dtw.cpp:83-85) written into the reference-base column of out_ll
 void nvbk_no_snp2(const ModelDev &M, const BatchDev &B, int b0, int b1, const int64_t *d_mat_base, const double *pF,
                   const int32_t *pX, const double *sF, const int32_t *sX, double *d_out_ll, cudaStream_t st);

@@ -1,0 +1,330 @@
+// rows5.cu -- forward / backward banded DP rows, scaled linear domain (dp3.cuh), ROTATING wavefront.
+//
+// Same rows as rows4.cu (Node::NextRow, node_next_row.h:6-61, driven by dtw.cpp:48-81,182-197), different schedule.
+// rows4.cu cuts the rows of a pass into stripes of 31 (A-row, B-row) pairs; inside a stripe the band drifts by ~10
+// columns per pair while the wavefront lags by one column per lane, so every lane idles for half of the stripe
+// (utilisation W / (W + 11*31) = 47 % at the default band).  Here ONE warp per (read, direction) runs one continuous
+// wavefront: pair g always works on column C0 +- (t - g) at step t, and lane g mod 32 takes pair g+32 as soon as
+// pair g has left its band -- nominally a pair is busy W+1 = 302 of every 352 steps (86 %).  Neighbour cells still
+// travel by warp shuffle (a rotation, lane 31 feeds lane 0), tagged with the pair index because a lane may already
+// have moved on.
+//
+// When a pair is not finished by the time its lane must start the next one (bands are irregular: ~5 % of the pairs
+// of a default read) the new pair starts in a SECOND slot of the lane, and the step body runs a second time, for the
+// whole warp, only while some lane has a live second slot.  Reads that would need a third slot (very wide or very
+// slowly drifting bands) are recognised by the band kernel (NVB_READ_NO_ROTATION) and go through rows4.cu.
+// Pairs change slots only at multiples of TS steps, so the store tiles (see rows4.cu) always hold one pair per lane.
+#include "dp3.cuh"
+#include "kernels.h"
+
+namespace {
+
+constexpr int TS = 4;       // steps per store tile; pairs are (de)activated only at multiples of TS
+constexpr int TSTRIDE = 5;  // padded tile row stride
+
+struct RowMeta {
+  long long off;  // offset of the row's first cell in the matrix planes
+  int s, e;       // band of the row (empty for lanes that store nothing)
+  int pair;       // pair index of the lane's slot: column at step t is C0 +- (t - pair)
+  int pad;
+};
+struct StoreTile {
+  double *f;      // [32][TSTRIDE]
+  int32_t *x;     // [32][TSTRIDE]
+  RowMeta *meta;  // [32]
+};
+constexpr size_t kTileBytes = 32 * TSTRIDE * (sizeof(double) + sizeof(int32_t)) + 32 * sizeof(RowMeta);
+
+template <bool REV>
+__device__ __forceinline__ void flush_tile(const StoreTile &tile, double *F, int32_t *X, int C0, int t0, int lane) {
+  constexpr int RPI = NVB_WARP / TS;  // rows per iteration
+  const int kk = lane & (TS - 1);
+#pragma unroll
+  for (int i = 0; i < NVB_WARP / RPI; i++) {
+    const int r = RPI * i + lane / TS;
+    const RowMeta m = tile.meta[r];
+    const int tt = t0 + kk;
+    const int c = REV ? C0 - (tt - m.pair) : C0 + (tt - m.pair);
+    if (c >= m.s && c <= m.e) {
+      const long long idx = m.off + (c - m.s);
+      F[idx] = tile.f[r * TSTRIDE + kk];
+      X[idx] = tile.x[r * TSTRIDE + kk];
+    }
+  }
+}
+
+// One (A-row, B-row) pair in flight in a lane.
+template <int MEL>
+struct Slot {
+  LaneCfg L;
+  LaneState<MEL> S;
+  LaneOut out;      // outputs of the last step (consumed by pair + 1 at the next step)
+  XD aout;
+  int pair;         // pair index g in sweep order, -1 = free
+  int t_end;        // last step with an in-band column
+  long long boff, aoff;
+  int ws, awe;      // A-row band for the stores of the transition sweep (empty when nothing is stored)
+  double x_next;    // signal sample of the next step, requested one step ahead
+};
+
+template <int MEL>
+__device__ __forceinline__ void slot_clear(Slot<MEL> &Q) {
+  lane_cfg_clear(Q.L);
+  lane_reset(Q.S);
+  Q.out.f = 0.0; Q.out.E = NVB_EZERO; Q.out.p = 1.0; Q.out.k = 0;
+  Q.aout = xd_zero();
+  Q.pair = -1; Q.t_end = -1; Q.boff = 0; Q.aoff = 0; Q.ws = 1; Q.awe = 0; Q.x_next = 0.0;
+}
+
+template <bool REV>
+__device__ __forceinline__ int pair_base(int n, int g) { return REV ? n - 1 - g : g; }
+
+// Steps at which pair g has its first / last in-band column (C0 = near end of the initial row's band).
+template <bool REV>
+__device__ __forceinline__ int pair_t_start(const ReadView &v, int C0, int g) {
+  const int i = pair_base<REV>(v.n, g);
+  return REV ? (C0 - v.be[i + 1]) + g : (v.bs[i] - C0) + g;
+}
+template <bool REV>
+__device__ __forceinline__ int pair_t_end(const ReadView &v, int C0, int g) {
+  const int i = pair_base<REV>(v.n, g);
+  return REV ? (C0 - v.bs[i]) + g : (v.be[i + 1] - C0) + g;
+}
+
+template <bool REV>
+__device__ __forceinline__ int sample_index(const ReadView &v, int C0, int g, int t) {
+  const int c = REV ? C0 - (t - g) : C0 + (t - g);
+  return min(max(REV ? c : c - 1, 0), v.N - 1);
+}
+
+template <int MEL, int MODE, bool REV>
+__device__ __forceinline__ void slot_start(Slot<MEL> &Q, const ModelDev &M, const ReadView &v, int C0, int g, int t) {
+  const int n = v.n;
+  const int i = pair_base<REV>(n, g);
+  const double C_E2 = 0.1353352832366127;  // exp(-2): the "/ 2" of kmer_model.cpp:60 is "- 2.0" in log space
+  slot_clear(Q);
+  Q.pair = g;
+  Q.t_end = pair_t_end<REV>(v, C0, g);
+  Q.x_next = __ldg(v.sig + sample_index<REV>(v, C0, g, t));
+  const bool hasA = (MODE != NVB_MODE_PLAIN) && (REV ? (i <= n - 2) : (i >= 1));
+  const int aband = REV ? i + 1 : i, bband = REV ? i : i + 1, nb = REV ? i + 1 : i - 1;
+  const int id = kmer_id(M, v, i, INT32_MIN, 0);
+  Q.L.role = NVB_ROLE_PAIR;
+  Q.L.mu = M.mean[id]; Q.L.ac = M.ac[id]; Q.L.mc = M.mc[id];
+  Q.L.ms = v.bs[bband]; Q.L.me = v.be[bband];
+  if (MODE == NVB_MODE_TRANS) {
+    Q.aoff = trans_row_off(v, REV ? 2 * i + 1 : 2 * i);
+    Q.boff = trans_row_off(v, REV ? 2 * i : 2 * i + 1);
+  } else {
+    Q.boff = v.coff[bband];
+  }
+  if (hasA) {
+    Q.L.ws = v.bs[aband]; Q.L.we = v.be[aband];
+    if (MODE == NVB_MODE_TRANS) {  // GetTransitionDistribution (kmer_model.cpp:64-94): constant 0.01, or 0
+      Q.ws = Q.L.ws; Q.awe = Q.L.we;
+      const double mo = M.mean[kmer_id(M, v, nb, INT32_MIN, 0)];
+      const bool dead = (mo == Q.L.mu);
+      Q.L.pc = dead ? 0.0 : 0.01 * 64.0;  // 0.01 as mantissa 0.64 and exponent -6 (an exact rescaling)
+      Q.L.kc = dead ? NVB_EZERO : -6;
+    } else {
+      Q.L.cm = C_E2; Q.L.abias = 0;
+    }
+  }
+}
+
+// One step of one slot.  `pf .. pk, ptag` = outputs of the producer lane's slot(s) at the previous step.
+template <int MEL, int MODE, bool REV>
+__device__ __forceinline__ void slot_step(Slot<MEL> &Q, const ReadView &v, int C0, int t, const LaneOut &in0, int tag0,
+                                          const LaneOut &in1, int tag1, bool have1, int ones_s, int ones_e) {
+  const int g = Q.pair;
+  const int c = REV ? C0 - (t - g) : C0 + (t - g);
+  const double x = Q.x_next;
+  Q.x_next = __ldg(v.sig + sample_index<REV>(v, C0, g, t + 1));
+  LaneOut in;
+  const int want = g - 1;
+  if (g == 0) {  // the all-ones initial row (dtw.cpp:50,66,182,190)
+    const bool inb = c >= ones_s && c <= ones_e;
+    in.f = inb ? 1.0 : 0.0; in.E = inb ? 0 : NVB_EZERO; in.p = 1.0; in.k = 0;
+  } else if (tag0 == want) {
+    in = in0;
+  } else if (have1 && tag1 == want) {
+    in = in1;
+  } else {  // the producer has left its band: nothing flows any more
+    in.f = 0.0; in.E = NVB_EZERO; in.p = 1.0; in.k = 0;
+  }
+  lane_step<MEL, MODE, false, -1, false>(Q.L, Q.S, c, x, in, 1.0, 0, Q.out, Q.aout);
+}
+
+template <int MODE>
+__device__ __forceinline__ LaneOut rotate_out(const LaneOut &o, int src) {
+  LaneOut r;
+  r.f = __shfl_sync(NVB_FULL, o.f, src);
+  r.E = __shfl_sync(NVB_FULL, o.E, src);
+  if (MODE == NVB_MODE_WOBBLE) {
+    r.p = __shfl_sync(NVB_FULL, o.p, src);
+    r.k = __shfl_sync(NVB_FULL, o.k, src);
+  } else {
+    r.p = 1.0; r.k = 0;
+  }
+  return r;
+}
+
+template <int MEL>
+__device__ __forceinline__ void write_meta(const StoreTile &tb, const StoreTile &ta, const Slot<MEL> &Q, int lane,
+                                           bool trans) {
+  RowMeta m;
+  const bool live = Q.pair >= 0;
+  m.off = Q.boff; m.s = live ? Q.L.ms : 1; m.e = live ? Q.L.me : 0; m.pair = live ? Q.pair : 0; m.pad = 0;
+  tb.meta[lane] = m;
+  if (trans) {
+    m.off = Q.aoff; m.s = live ? Q.ws : 1; m.e = live ? Q.awe : 0;
+    ta.meta[lane] = m;
+  }
+}
+
+template <int MEL, int MODE, bool REV>
+__device__ void sweep_rotate(const ModelDev &M, const ReadView &v, double *F, int32_t *X, int lane,
+                             const StoreTile (&tiles)[4]) {
+  const int n = v.n;
+  constexpr bool TRANS = (MODE == NVB_MODE_TRANS);
+  const StoreTile &tPB = tiles[0], &tPA = tiles[1], &tSB = tiles[2], &tSA = tiles[3];
+
+  // all-ones first row (dtw.cpp:50,66,182,190): written to HBM here, generated on the fly for pair 0
+  const int j0 = REV ? n : 0;
+  const int ones_s = v.bs[j0], ones_e = v.be[j0];
+  {
+    const int64_t off0 = REV ? (TRANS ? trans_row_off(v, 2 * n - 1) : v.coff[n]) : 0;
+    for (int c = ones_s + lane; c <= ones_e; c += NVB_WARP) { F[off0 + c - ones_s] = 1.0; X[off0 + c - ones_s] = 0; }
+  }
+  const int C0 = REV ? ones_e : ones_s;
+  const int T_total = ((pair_t_end<REV>(v, C0, n - 1) + 1 + TS - 1) / TS) * TS;
+
+  Slot<MEL> P, Q2;
+  slot_clear(P);
+  slot_clear(Q2);
+  int next_g = lane;                                   // next pair this lane will take
+  int next_start = (next_g < n) ? pair_t_start<REV>(v, C0, next_g) : 0x7fffffff;
+  bool any2_tile = false;                              // some lane had a live second slot during this tile
+
+  for (int t = 0; t < T_total; t++) {
+    if ((t & (TS - 1)) == 0) {
+      // ---- slot management, only at tile boundaries -----------------------------------------------------------
+      // a pair keeps its slot until the step AFTER its last in-band one: that is when its last cell is consumed
+      if (P.pair >= 0 && t >= P.t_end + 2) {
+        if (Q2.pair >= 0) { P = Q2; slot_clear(Q2); } else slot_clear(P);
+      }
+      if (next_start < t + TS) {  // its first in-band column falls into this tile
+        if (P.pair < 0) slot_start<MEL, MODE, REV>(P, M, v, C0, next_g, t);
+        else slot_start<MEL, MODE, REV>(Q2, M, v, C0, next_g, t);  // the band kernel guarantees Q2 is free
+        next_g += NVB_WARP;
+        next_start = (next_g < n) ? pair_t_start<REV>(v, C0, next_g) : 0x7fffffff;
+      }
+      any2_tile = __any_sync(NVB_FULL, Q2.pair >= 0);
+      write_meta(tPB, tPA, P, lane, TRANS);
+      if (any2_tile) write_meta(tSB, tSA, Q2, lane, TRANS);
+      __syncwarp();
+    }
+    // ---- neighbour outputs of the previous step: rotation by one lane, tagged with the pair index -----------------
+    const int src = (lane + NVB_WARP - 1) & (NVB_WARP - 1);
+    const LaneOut in0 = rotate_out<MODE>(P.out, src);
+    const int tag0 = __shfl_sync(NVB_FULL, P.pair, src);
+    LaneOut in1;
+    in1.f = 0.0; in1.E = NVB_EZERO; in1.p = 1.0; in1.k = 0;
+    int tag1 = -1;
+    if (any2_tile) {
+      in1 = rotate_out<MODE>(Q2.out, src);
+      tag1 = __shfl_sync(NVB_FULL, Q2.pair, src);
+    }
+    // ---- the step(s) ------------------------------------------------------------------------------------------------
+    const int k = t & (TS - 1);
+    if (P.pair >= 0) slot_step<MEL, MODE, REV>(P, v, C0, t, in0, tag0, in1, tag1, any2_tile, ones_s, ones_e);
+    tPB.f[lane * TSTRIDE + k] = P.out.f;
+    tPB.x[lane * TSTRIDE + k] = P.out.E;
+    if (TRANS) { tPA.f[lane * TSTRIDE + k] = P.aout.f; tPA.x[lane * TSTRIDE + k] = P.aout.e; }
+    if (any2_tile) {
+      if (Q2.pair >= 0) slot_step<MEL, MODE, REV>(Q2, v, C0, t, in0, tag0, in1, tag1, true, ones_s, ones_e);
+      tSB.f[lane * TSTRIDE + k] = Q2.out.f;
+      tSB.x[lane * TSTRIDE + k] = Q2.out.E;
+      if (TRANS) { tSA.f[lane * TSTRIDE + k] = Q2.aout.f; tSA.x[lane * TSTRIDE + k] = Q2.aout.e; }
+    }
+    if (k == TS - 1) {
+      __syncwarp();
+      flush_tile<REV>(tPB, F, X, C0, t - k, lane);
+      if (TRANS) flush_tile<REV>(tPA, F, X, C0, t - k, lane);
+      if (any2_tile) {
+        flush_tile<REV>(tSB, F, X, C0, t - k, lane);
+        if (TRANS) flush_tile<REV>(tSA, F, X, C0, t - k, lane);
+      }
+      __syncwarp();
+    }
+    if ((t & NVB_RENORM_MASK) == NVB_RENORM_MASK) {
+      lane_renorm(P.S);
+      if (any2_tile) lane_renorm(Q2.S);
+    }
+  }
+}
+
+template <int MEL, int MODE>
+__global__ void __launch_bounds__(64, 8) sweep5_kernel(ModelDev M, BatchDev B, int b0, int n_items,
+                                                     const int64_t *mat_base, double *pF, int32_t *pX, double *sF,
+                                                     int32_t *sX) {
+  extern __shared__ unsigned long long smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * (blockDim.x >> 5) + warp;  // (read, direction)
+  if (item >= n_items) return;
+  const int b = b0 + (item >> 1);
+  if (B.flags[b] != 0) return;  // bad band
+  unsigned char *base = reinterpret_cast<unsigned char *>(smem_raw) + (size_t)warp * 4 * kTileBytes;
+  StoreTile tiles[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    unsigned char *p = base + (size_t)i * kTileBytes;
+    tiles[i].f = reinterpret_cast<double *>(p);
+    tiles[i].meta = reinterpret_cast<RowMeta *>(tiles[i].f + 32 * TSTRIDE);
+    tiles[i].x = reinterpret_cast<int32_t *>(tiles[i].meta + 32);
+  }
+  ReadView v = read_view(B, b);
+  const int64_t mb = mat_base[b];
+  if (item & 1) sweep_rotate<MEL, MODE, true>(M, v, sF + mb, sX + mb, lane, tiles);
+  else sweep_rotate<MEL, MODE, false>(M, v, pF + mb, pX + mb, lane, tiles);
+}
+
+template <int MEL, int MODE>
+void launch_mode(const ModelDev &M, const BatchDev &B, int b0, int n_items, const int64_t *mb, double *pF, int32_t *pX,
+                 double *sF, int32_t *sX, cudaStream_t st) {
+  const int warps = 2;  // 2 x 4 tiles x 2.4 KB = 19 KB per CTA
+  const size_t smem = (size_t)warps * 4 * kTileBytes;
+  sweep5_kernel<MEL, MODE><<<(n_items + warps - 1) / warps, warps * NVB_WARP, smem, st>>>(M, B, b0, n_items, mb, pF, pX,
+                                                                                         sF, sX);
+}
+
+template <int MEL>
+void launch_sweep5(const ModelDev &M, const BatchDev &B, int mode, int b0, int n_items, const int64_t *mb, double *pF,
+                   int32_t *pX, double *sF, int32_t *sX, cudaStream_t st) {
+  switch (mode) {
+    case NVB_MODE_PLAIN: launch_mode<MEL, NVB_MODE_PLAIN>(M, B, b0, n_items, mb, pF, pX, sF, sX, st); break;
+    case NVB_MODE_TRANS: launch_mode<MEL, NVB_MODE_TRANS>(M, B, b0, n_items, mb, pF, pX, sF, sX, st); break;
+    default: launch_mode<MEL, NVB_MODE_WOBBLE>(M, B, b0, n_items, mb, pF, pX, sF, sX, st); break;
+  }
+}
+
+}  // namespace
+
+// Rotating-wavefront sweep of the reads [b0, b1) whose flag is NVB_READ_OK.  Returns -1 for an unsupported
+// min_event_length.
+int nvbk_sweep_rotate(const ModelDev &M, const BatchDev &B, int mode, int b0, int b1, const int64_t *d_mat_base,
+                      double *pF, int32_t *pX, double *sF, int32_t *sX, cudaStream_t st) {
+  const int n_items = 2 * (b1 - b0);
+  if (n_items <= 0) return 0;
+  switch (B.mel) {
+    case 0: launch_sweep5<0>(M, B, mode, b0, n_items, d_mat_base, pF, pX, sF, sX, st); break;
+    case 1: launch_sweep5<1>(M, B, mode, b0, n_items, d_mat_base, pF, pX, sF, sX, st); break;
+    case 2: launch_sweep5<2>(M, B, mode, b0, n_items, d_mat_base, pF, pX, sF, sX, st); break;
+    case 3: launch_sweep5<3>(M, B, mode, b0, n_items, d_mat_base, pF, pX, sF, sX, st); break;
+    case 4: launch_sweep5<4>(M, B, mode, b0, n_items, d_mat_base, pF, pX, sF, sX, st); break;
+    case 5: launch_sweep5<5>(M, B, mode, b0, n_items, d_mat_base, pF, pX, sF, sX, st); break;
+    case 6: launch_sweep5<6>(M, B, mode, b0, n_items, d_mat_base, pF, pX, sF, sX, st); break;
+    default: return -1;
+  }
+  return 0;
+}

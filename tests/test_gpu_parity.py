@@ -331,3 +331,29 @@ def test_large_kmer_models(lib_built, k, cp):
         ca = rng.integers(0, 4, size=k - cp - 1)
         return (mean, sigma, np.clip(sig, -5, 5), ref, cb, ca, anchors)
     _compare_batch(rng, [with_model(c) for c in cases], k, cp, mel, bw, mean, sigma)
+
+
+@pytest.fixture
+def sweep_schedule(request, monkeypatch):
+    """Force one of the two sweep schedules (the library picks by batch size otherwise): 'r' = rotating wavefront
+    (rows5.cu), 's' = pipelined stripes (rows4.cu)."""
+    monkeypatch.setenv('NVB_SWEEP', request.param)
+    return request.param
+
+
+@pytest.mark.parametrize('sweep_schedule', ['r', 's'], indirect=True)
+def test_both_sweep_schedules_match_oracle(lib_built, default_model, sweep_schedule):
+    """Every mode through both schedules: random ragged batches (sparse anchors, several minimum event lengths, reads
+    shorter and longer than one 32-pair generation) and full-size 6-mer reads on both strands."""
+    for k, cp, mel in ((3, 1, 2), (4, 2, 1), (2, 0, 3), (6, 2, 2)):
+        rng = np.random.default_rng(900 + 10 * k + mel)
+        bw = int(rng.integers(4, 24))
+        mean = rng.normal(0, 1.2, size=4 ** k)
+        sigma = rng.uniform(0.2, 0.6, size=4 ** k)
+        cases = []
+        for i in range(8):
+            n = int(rng.integers(1, 140)) if i else 1
+            c = make_case(rng, k, cp, n, bw, mel, sparse=i % 3 == 1)
+            cases.append((mean, sigma) + c[2:])
+        _compare_batch(rng, cases, k, cp, mel, bw, mean, sigma, exact=(k > 3))
+    test_default_model_read_matches_oracle(default_model)
