@@ -246,3 +246,21 @@ def test_meth_scores_match_reference_golden(golden_estimator, default_model_host
         assert [maxs3(f[2]) for f in feats] == g['meth/read%d/aggregated' % i].tolist()
         total += len(feats)
     assert total >= 10
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's own CPU path on the host cores) prints one JSON line with the
+    contract's keys; a tiny sample keeps the CPU suite fast."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--cpu-sample', '2',
+                          '--bases', '150', '--steps', '1', '--warmup', '1'], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])
+    assert line['impl'] == 'reference' and line['metric'] == 'signal_samples_aligned_per_sec'
+    assert line['unit'] == 'samples/s' and line['higher_is_better'] is True and line['value'] > 0
+    assert line['cpu_baseline']['kind'] in ('reference', 'port') and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e'] == {'value': line['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0,
+                           'd2h_bytes_per_step': 0}
+    assert 'workload' in line['config'] and line['vs_baseline'] is None
