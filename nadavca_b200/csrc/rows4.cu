@@ -13,7 +13,8 @@
 // NW+1 hand-off rows a buffer is re-used by the warp that consumed it last, so program order alone protects it.
 // The band of a default read (W = 301 columns, ~10 new columns per base) makes a 31-pair stripe last ~670 steps
 // while a new stripe can start every ~340 steps: two warps per direction keep every warp busy and halve the
-// critical path compared with draining each stripe (rows3.cu); wider bands use more warps.
+// critical path compared with draining each stripe (history/v3_rows_drained_stripes.cu.txt); wider bands use more
+// warps.  For batches that fill the GPU, rows5.cu (one rotating wavefront per direction) needs fewer steps.
 // Stored rows are written as (mantissa double, exponent int32) planes.
 #include <stdlib.h>
 #include "dp3.cuh"
