@@ -1,4 +1,4 @@
-// dp3.cuh -- the scaled linear-domain DP cell shared by the row sweep (rows3.cu) and the SNP kernel (snp3.cu).
+// dp3.cuh -- the scaled linear-domain DP cell shared by the row sweeps (rows4.cu, rows5.cu) and the SNP kernel (snp3.cu).
 //
 // The reference carries every DP cell as a log-probability and pays one exp + one log per cell
 // (probability.cpp:33-40).  Here a cell is a double mantissa f and an int32 binary exponent e,

@@ -19,7 +19,7 @@ int nvbk_sweep_rotate(const ModelDev &M, const BatchDev &B, int mode, int b0, in
 void nvbk_no_snp2(const ModelDev &M, const BatchDev &B, int b0, int b1, const int64_t *d_mat_base, const double *pF,
                   const int32_t *pX, const double *sF, const int32_t *sX, double *d_out_ll, cudaStream_t st);
 
-// snp2.cu: the SNP re-run loop (dtw.cpp:93-129)
+// snp3.cu: the SNP re-run loop (dtw.cpp:93-129)
 int nvbk_snp2(const ModelDev &M, const BatchDev &B, int wobbling, int b0, int b1, int64_t g0, int64_t g1,
               const int64_t *d_mat_base, const double *pF, const int32_t *pX, const double *sF, const int32_t *sX,
               double *d_out_ll, cudaStream_t st);

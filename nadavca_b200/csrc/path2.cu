@@ -4,7 +4,7 @@
 // PathSearchingNode::NextRow / GetBestIndex / GetPrevious (node.cpp:39-91).
 //
 // Stage 1, score_kernel (fully parallel, HBM-bound): score = log(prefix * suffix) for every stored cell, formed
-//   from the (mantissa, exponent) planes written by rows2.cu and written over the prefix mantissa plane.
+//   from the (mantissa, exponent) planes written by the sweeps (rows4.cu, rows5.cu) and written over the prefix mantissa plane.
 // Stage 2, path2_kernel (one warp per read, rows in order): dp[r][c] = score[r][c] + max_{i' <= c - m} dp[r-1][i'].
 //   The running "best predecessor" of the reference (node.cpp:68-89) is a prefix maximum of the previous dp row; it
 //   is kept in shared memory as M[i] = max(dp[r-1][..i]) so a row is: K consecutive columns per lane, K lookups,
