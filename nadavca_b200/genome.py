@@ -16,7 +16,13 @@ def _as_bytes(sequence):
         return numpy.frombuffer(sequence.encode('ascii'), dtype=numpy.uint8)
     arr = numpy.asarray(sequence)
     if arr.dtype.kind == 'U':
-        return arr.astype('S1').view(numpy.uint8) if arr.size else numpy.zeros(0, dtype=numpy.uint8)
+        if arr.size == 0:
+            return numpy.zeros(0, dtype=numpy.uint8)
+        if arr.dtype.itemsize == 4:  # arrays of single characters: read the UCS4 code points directly
+            codes = numpy.ascontiguousarray(arr).view(numpy.uint32)
+            if codes.max() < 256:
+                return codes.astype(numpy.uint8)
+        return arr.astype('S1').view(numpy.uint8)
     if arr.dtype.kind == 'S':
         return arr.view(numpy.uint8)
     return arr.astype(numpy.uint8)
@@ -48,7 +54,7 @@ class Genome:
         for value in numpy.unique(raw):
             if chr(int(value)) not in complement:
                 raise KeyError(chr(int(value)))
-        return _COMP[raw][::-1].copy().view('S1').astype('U1')
+        return _COMP[raw][::-1].astype(numpy.uint32).view('U1')  # UCS4 code points -> array of 1-char strings
 
     @staticmethod
     def load_from_fasta(filename):
