@@ -355,3 +355,26 @@ def test_detect_meth_api(golden_estimator, default_model, tmp_path):
             assert len(context) == 11 and context[5:7] == 'CG' and len(scores) == 11
             want.append(('r%d' % i, pos, context, ','.join(map(str, scores)), maxs3(scores)))
     assert rows == want
+
+
+def test_bench_line_contract():
+    """bench.py on a tiny workload prints one JSON line with every key of the measurement contract."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--reads', '24', '--bases', '400', '--steps',
+                          '2', '--warmup', '3', '--cpu-sample', '2'], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'e2e', 'gpu_launches', 'clocks', 'roofline', 'cpu_baseline'):
+        assert key in line, key
+    assert line['n_gpus'] == 1 and line['steps'] == 2 and line['dtype'] == 'f64' and line['data'] == 'synthetic'
+    assert line['value'] > 0 and line['e2e']['value'] > 0 and line['e2e']['h2d_bytes_per_step'] > 0
+    assert line['gpu_launches'] >= 2 * 8  # sweeps, score, path, no-SNP, SNP, chunk, scatter, posterior per step
+    assert set(line['roofline']) >= {'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'}
+    assert line['roofline']['bound'] == 'hbm' and 0 < line['roofline']['frac'] < 1
+    assert line['cpu_baseline']['kind'] in ('reference', 'port') and line['cpu_baseline']['cores'] >= 1
+    assert 'workload' in line['config'] and line['pipelined']['value'] > 0
