@@ -369,7 +369,8 @@ int run_sweep(nvb_batch *b, int mode, const Wave &w, cudaStream_t st) {
   // sweep hides latency better, with more the second wave eats the gain.
   const int items = 2 * (w.b1 - w.b0);
   const int resident = b->model->sm_count * 16;
-  bool rotate = w.maxw <= 640 && 10 * items >= 6 * resident && items <= resident;
+  // (the transition sweep stores twice the rows and gains nothing from rotating: 68 against 67 ms at 1000 reads)
+  bool rotate = mode != NVB_MODE_TRANS && w.maxw <= 640 && 10 * items >= 6 * resident && items <= resident;
   if (const char *env = getenv("NVB_SWEEP")) rotate = w.maxw <= 640 && env[0] == 'r';  // experiments: r / s
   for (int i = w.b0; i < w.b1 && rotate; i++) rotate = !b->no_rotation[i];
   if (rotate)
