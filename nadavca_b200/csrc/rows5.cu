@@ -19,6 +19,10 @@
 
 namespace {
 
+#ifndef NVB_ROT_MIN_BLOCKS
+#define NVB_ROT_MIN_BLOCKS 8  // 64-thread CTAs per SM: 128 registers per thread, 16 warps per SM
+#endif
+
 constexpr int TS = 4;       // steps per store tile; pairs are (de)activated only at multiples of TS
 constexpr int TSTRIDE = 5;  // padded tile row stride
 
@@ -265,7 +269,7 @@ __device__ void sweep_rotate(const ModelDev &M, const ReadView &v, double *F, in
 }
 
 template <int MEL, int MODE>
-__global__ void __launch_bounds__(64, 8) sweep5_kernel(ModelDev M, BatchDev B, int b0, int n_items,
+__global__ void __launch_bounds__(64, NVB_ROT_MIN_BLOCKS) sweep5_kernel(ModelDev M, BatchDev B, int b0, int n_items,
                                                      const int64_t *mat_base, double *pF, int32_t *pX, double *sF,
                                                      int32_t *sX) {
   extern __shared__ unsigned long long smem_raw[];
