@@ -200,12 +200,13 @@ def _cpu_worker_init(k, cp, mean, sigma, backend):
 
 
 def _cpu_worker(task):
-    """The two DP calls of estimator.py:77-109 for one read on one core."""
+    """The two DP calls of estimator.py:77-109 for one read on one core; the results go back to the parent, which
+    checks the GPU's results for the same reads against them (the `parity` block of the bench line)."""
     orc, model = _WORKER['orc'], _WORKER['model']
     signal, tweaked, ref, cb, ca, anchors, bw, mel = task
     ev = orc.refine_alignment(signal, ref, cb, ca, anchors, bw, mel, model, False)
     ll = orc.estimate_log_likelihoods(tweaked, ref, cb, ca, anchors, bw, mel, model, True)
-    return len(ev), len(ll)
+    return np.asarray(ev, dtype=np.int32).reshape(-1, 2), np.asarray(ll, dtype=np.float64)
 
 
 class CpuArm:
@@ -221,7 +222,7 @@ class CpuArm:
 
     def run(self, tasks):
         t0 = time.perf_counter()
-        self.pool.map(_cpu_worker, tasks, chunksize=1)
+        self.results = self.pool.map(_cpu_worker, tasks, chunksize=1)
         return time.perf_counter() - t0
 
     def close(self):
@@ -392,6 +393,10 @@ def run_ours(args):
     tn, tt = batch_n.timing(), batch_t.timing()
     batch_n.enable_timing(False)
     batch_t.enable_timing(False)
+    # what the timed steps left resident for the reads of the CPU sample (checked against the reference below)
+    n_check = cpu_sample_size(args, len(items)) if (world == 1 and not args.no_cpu_baseline) else 0
+    gpu_events = batch_n.events()[0][:n_check] if n_check else []
+    gpu_ll = batch_t.log_likelihoods()[0][:n_check] if n_check else []
 
     # ---- software pipeline over consecutive batches (reported next to `value`, never instead of it) --------------
     # In a job of many batches the refine stage of batch k+1 does not depend on the estimate stage of batch k.  With
@@ -530,7 +535,7 @@ def run_ours(args):
                        'estimate stage; same kernels and work per step as `value`'},
         }
         if world == 1 and not args.no_cpu_baseline:
-            line['cpu_baseline'] = cpu_baseline(km, items, tweaked, args, mel)
+            line['cpu_baseline'], line['parity'] = cpu_baseline(km, items, tweaked, args, mel, gpu_events, gpu_ll)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -548,16 +553,48 @@ def ncu_traffic(reads_per_gpu):
         return None
 
 
-def cpu_baseline(km, items, tweaked, args, mel):
+def cpu_sample_size(args, n_items):
+    """Reads of the CPU leg: at least 64 (a multiple of the host cores, so that every core is busy to the end)."""
     cores = os.cpu_count() or 1
-    n_sample = min(len(items), args.cpu_sample or cores)
+    want = args.cpu_sample or max(64, cores)
+    if not args.cpu_sample and want % cores:
+        want += cores - want % cores
+    return min(n_items, want)
+
+
+def cpu_baseline(km, items, tweaked, args, mel, gpu_events, gpu_ll):
+    """The reference's CPU implementation on the first reads of the benchmarked workload, timed on the host cores,
+    and -- with its results -- the check of what the GPU computed for the same reads during the timed steps."""
+    from oracle import oracle as orc
+    from oracle import parity
+    cores = os.cpu_count() or 1
+    n_sample = cpu_sample_size(args, len(items))
     tasks = cpu_tasks(km, items[:n_sample], tweaked[:n_sample], args.bandwidth, mel)
     arm = CpuArm(km, min(cores, n_sample), method='spawn')  # CUDA is initialised in this process: do not fork
     t = arm.run(tasks)
+    results = arm.results
     arm.close()
     samples = sum(len(it['signal']) for it in items[:n_sample])
-    return {'value': samples / t, 'unit': 'samples/s', 'cores': arm.cores, 'kind': arm.kind,
+    base = {'value': samples / t, 'unit': 'samples/s', 'cores': arm.cores, 'kind': arm.kind,
             'sample': 'first %d reads of the workload, one per worker process, %.1f s wall' % (n_sample, t)}
+    om = orc.OracleModel(km.get_k(), km.get_central_position(), 4, km.mean, km.sigma, 'port')
+    par = {'reads': n_sample, 'against': arm.kind, 'event_mismatches': 0, 'tie_accepts': 0, 'max_ll_rel': 0.0,
+           'll_mismatches': 0, 'events_compared': 0, 'll_rtol': 1e-9}
+    for i, (task, (ev, ll)) in enumerate(zip(tasks, results)):
+        signal, _, ref, cb, ca, anchors, bw, _ = task
+        par['events_compared'] += len(ev)
+        try:
+            kind = parity.compare_events(gpu_events[i], signal, ref, cb, ca, anchors, bw, mel, om, False, want=ev)
+            par['tie_accepts'] += kind == 'tie'
+        except AssertionError:
+            par['event_mismatches'] += 1
+        try:
+            rel = parity.ll_max_rel(gpu_ll[i], ll)
+            par['max_ll_rel'] = max(par['max_ll_rel'], rel)
+            par['ll_mismatches'] += rel > par['ll_rtol']
+        except AssertionError:
+            par['ll_mismatches'] += 1
+    return base, par
 
 
 def relaunch_under_torchrun(args):

@@ -45,6 +45,14 @@ int nvb_device_count(void);
 /* Device buffers of destroyed batches / models are kept in a per-device cache for re-use (cudaFree costs far more
  * than a batch's kernels); this hands the cached blocks back to the driver. */
 int nvb_trim_memory(int device);
+/* Schedule of the forward / backward row sweeps (a tuning knob without a reference counterpart; results are
+ * identical): AUTO picks per wave by batch size, ROTATE = one rotating wavefront per (read, direction), STRIPES =
+ * pipelined 31-row stripes.  The environment variable NVB_SWEEP=r|s sets the initial value when the library is
+ * loaded.  Returns the previous setting. */
+#define NVB_SWEEP_AUTO 0
+#define NVB_SWEEP_ROTATE 1
+#define NVB_SWEEP_STRIPES 2
+int nvb_set_sweep_schedule(int schedule);
 
 /* ---- k-mer model: replaces class KmerModel (dtwmodule.cpp:12-18, kmer_model.cpp:6-42) -------------------- */
 /* mean/sigma have alphabet_size^k entries; tables (mean, log(1/sqrt(2 pi s^2)), 1/(2 s^2)) are built on the host

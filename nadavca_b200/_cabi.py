@@ -42,6 +42,7 @@ SIGNATURES = {
     'nvb_last_error': (ctypes.c_char_p, []),
     'nvb_device_count': (ctypes.c_int, []),
     'nvb_trim_memory': (ctypes.c_int, [ctypes.c_int]),
+    'nvb_set_sweep_schedule': (ctypes.c_int, [ctypes.c_int]),
     'nvb_model_create': (ctypes.c_void_p, [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f64p, c_f64p, ctypes.c_int64,
                                            ctypes.c_int]),
     'nvb_model_destroy': (None, [ctypes.c_void_p]),

@@ -19,6 +19,20 @@ namespace {
 
 thread_local std::string g_err;
 
+// Tuning / debugging switches: the environment is read ONCE, when the library is loaded; nvb_set_sweep_schedule
+// changes the schedule at run time (tests force both schedules through it).
+struct Options {
+  int sweep = NVB_SWEEP_AUTO;   // NVB_SWEEP=r|s
+  bool skip_path = false;       // NVB_DEBUG_SKIP_PATH: keep the prefix plane for nvb_batch_debug_rows
+  int sweep_warps = 0;          // NVB_SWEEP_WARPS: warps per (read, direction) of the striped sweep, 0 = automatic
+  Options() {
+    if (const char *env = getenv("NVB_SWEEP")) sweep = env[0] == 'r' ? NVB_SWEEP_ROTATE : (env[0] == 's' ? NVB_SWEEP_STRIPES : NVB_SWEEP_AUTO);
+    skip_path = getenv("NVB_DEBUG_SKIP_PATH") != nullptr;
+    if (const char *env = getenv("NVB_SWEEP_WARPS")) sweep_warps = atoi(env);
+  }
+};
+Options g_opt;
+
 int fail(int code, const char *fmt, ...) {
   char buf[512];
   va_list ap;
@@ -201,6 +215,12 @@ int nvb_abi_version(void) { return 1; }
 
 const char *nvb_last_error(void) { return g_err.c_str(); }
 
+int nvb_set_sweep_schedule(int schedule) {
+  const int before = g_opt.sweep;
+  if (schedule == NVB_SWEEP_AUTO || schedule == NVB_SWEEP_ROTATE || schedule == NVB_SWEEP_STRIPES) g_opt.sweep = schedule;
+  return before;
+}
+
 int nvb_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -371,11 +391,12 @@ int run_sweep(nvb_batch *b, int mode, const Wave &w, cudaStream_t st) {
   const int resident = b->model->sm_count * 16;
   // (the transition sweep stores twice the rows and gains nothing from rotating: 68 against 67 ms at 1000 reads)
   bool rotate = mode != NVB_MODE_TRANS && w.maxw <= 640 && 10 * items >= 6 * resident && items <= resident;
-  if (const char *env = getenv("NVB_SWEEP")) rotate = w.maxw <= 640 && env[0] == 'r';  // experiments: r / s
+  if (g_opt.sweep != NVB_SWEEP_AUTO) rotate = w.maxw <= 640 && g_opt.sweep == NVB_SWEEP_ROTATE;
   for (int i = w.b0; i < w.b1 && rotate; i++) rotate = !b->no_rotation[i];
   if (rotate)
     return nvbk_sweep_rotate(M, b->dev, mode, w.b0, w.b1, b->d_mat_base.p, ws.pF.p, ws.pX.p, ws.sF.p, ws.sX.p, st);
-  return nvbk_sweep2(M, b->dev, mode, w.b0, w.b1, w.maxw, b->d_mat_base.p, ws.pF.p, ws.pX.p, ws.sF.p, ws.sX.p, st);
+  return nvbk_sweep2(M, b->dev, mode, w.b0, w.b1, w.maxw, g_opt.sweep_warps, b->d_mat_base.p, ws.pF.p, ws.pX.p, ws.sF.p,
+                     ws.sX.p, st);
 }
 
 int64_t matrix_cells(const nvb_batch *b, int i, int mode) {
@@ -541,7 +562,7 @@ int nvb_batch_refine(nvb_batch *b, int model_transitions, void *stream) {
       if (src == -1) return fail(NVB_EINVAL, "min_event_length %d is not supported (maximum 6)", b->dev.mel);
       if (src) return fail(NVB_ENOMEM, "band row of %d columns does not fit the sweep's shared-memory hand-off rows", w.maxw);
     }
-    if (!getenv("NVB_DEBUG_SKIP_PATH")) {  // debugging aid: keep the prefix plane for nvb_batch_debug_rows
+    if (!g_opt.skip_path) {  // debugging aid: keep the prefix plane for nvb_batch_debug_rows
       StageTimer t(b, 1, st);
       nvbk_score(w.cells, b->model->ws.pF.p, b->model->ws.pX.p, b->model->ws.sF.p, b->model->ws.sX.p, st);
       if (nvbk_path2(b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->model->ws.pF.p, b->model->ws.records.p, b->d_rec_base.p,

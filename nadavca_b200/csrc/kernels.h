@@ -9,7 +9,7 @@ void nvbk_expected_signal(const ModelDev &M, const BatchDev &B, int64_t total, d
 // rows4.cu: forward + backward banded rows for reads [b0,b1): one CTA per (read, direction), stripes pipelined over
 // its warps; rows are stored as a mantissa plane (double) and an exponent plane (int32).  wave_maxw = widest band
 // row of the wave.  Returns -1 for an unsupported min_event_length, -2 when the hand-off rows do not fit shared memory.
-int nvbk_sweep2(const ModelDev &M, const BatchDev &B, int mode, int b0, int b1, int wave_maxw,
+int nvbk_sweep2(const ModelDev &M, const BatchDev &B, int mode, int b0, int b1, int wave_maxw, int force_warps,
                 const int64_t *d_mat_base, double *pF, int32_t *pX, double *sF, int32_t *sX, cudaStream_t st);
 // rows5.cu: the same rows with one continuously rotating wavefront per (read, direction); for reads whose bands allow
 // it (band.cu flags the others).  Returns -1 for an unsupported min_event_length.

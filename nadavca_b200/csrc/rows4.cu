@@ -16,7 +16,6 @@
 // critical path compared with draining each stripe (history/v3_rows_drained_stripes.cu.txt); wider bands use more
 // warps.  For batches that fill the GPU, rows5.cu (one rotating wavefront per direction) needs fewer steps.
 // Stored rows are written as (mantissa double, exponent int32) planes.
-#include <stdlib.h>
 #include "dp3.cuh"
 #include "kernels.h"
 
@@ -349,7 +348,7 @@ int launch_sweep4(const ModelDev &M, const BatchDev &B, int mode, int b0, int n_
 
 // wave_maxw: widest band row among the reads [b0, b1).  Returns -1 for an unsupported min_event_length, -2 when the
 // shared-memory reservation fails.
-int nvbk_sweep2(const ModelDev &M, const BatchDev &B, int mode, int b0, int b1, int wave_maxw,
+int nvbk_sweep2(const ModelDev &M, const BatchDev &B, int mode, int b0, int b1, int wave_maxw, int force_warps,
                 const int64_t *d_mat_base, double *pF, int32_t *pX, double *sF, int32_t *sX, cudaStream_t st) {
   const int n_items = 2 * (b1 - b0);
   if (n_items <= 0) return 0;
@@ -357,7 +356,7 @@ int nvbk_sweep2(const ModelDev &M, const BatchDev &B, int mode, int b0, int b1, 
   const int width = (wave_maxw + 1) & ~1;  // keeps the int32 plane 8-byte aligned
   int NW = (wave_maxw + 12 * PAIRS + 11 * PAIRS - 1) / (11 * PAIRS);
   NW = NW < 1 ? 1 : (NW > 7 ? 7 : NW);
-  if (const char *env = getenv("NVB_SWEEP_WARPS")) NW = atoi(env) < 1 ? 1 : (atoi(env) > 7 ? 7 : atoi(env));  // experiments
+  if (force_warps > 0) NW = force_warps > 7 ? 7 : force_warps;  // experiments (NVB_SWEEP_WARPS, read at load)
   const int tiles_per_warp = (mode == NVB_MODE_TRANS) ? 2 : 1;
   auto bytes = [&](int nw) {
     return (size_t)64 + (size_t)(nw + 1) * width * (sizeof(double) + sizeof(int32_t)) +

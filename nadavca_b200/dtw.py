@@ -287,6 +287,21 @@ class Batch:
         return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(self.STAGES)}
 
 
+SWEEP_SCHEDULES = {None: 0, 'auto': 0, 'r': 1, 'rotate': 1, 's': 2, 'stripes': 2}
+
+
+def set_sweep_schedule(schedule):
+    """Force the schedule of the row sweeps ('r' rotating wavefront, 's' pipelined stripes, None automatic); returns
+    the previous setting as an int.  Results do not depend on it."""
+    return int(_cabi.load().nvb_set_sweep_schedule(SWEEP_SCHEDULES[schedule]))
+
+
+def trim_memory(device=None):
+    """Hand the library's cached device blocks back to the driver (nvb_trim_memory)."""
+    lib = _cabi.require_device()
+    _cabi.check(lib.nvb_trim_memory(_current_device() if device is None else int(device)), 'nvb_trim_memory')
+
+
 def measure_fp64_fma_rate(device=0):
     """FP64 FMA/s of the device (nvb_measure_fp64_fma_rate)."""
     lib = _cabi.require_device()

@@ -378,3 +378,7 @@ def test_bench_line_contract():
     assert line['roofline']['bound'] == 'hbm' and 0 < line['roofline']['frac'] < 1
     assert line['cpu_baseline']['kind'] in ('reference', 'port') and line['cpu_baseline']['cores'] >= 1
     assert 'workload' in line['config'] and line['pipelined']['value'] > 0
+    # the benchmarked reads themselves are checked against the reference inside the CPU leg
+    par = line['parity']
+    assert par['reads'] == 2 and par['event_mismatches'] == 0 and par['ll_mismatches'] == 0
+    assert par['events_compared'] > 0 and par['max_ll_rel'] < 1e-9

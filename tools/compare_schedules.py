@@ -15,7 +15,7 @@ lists = ([it['signal'] for it in items], [it['reference'] for it in items], [it[
 res = {}
 with dtw.Batch(km, *lists, bw, 2) as b:
     for sched in ('s', 'r'):
-        os.environ['NVB_SWEEP'] = sched
+        dtw.set_sweep_schedule(sched)
         out = {}
         for flag in (False, True):
             b.refine(flag); torch.cuda.synchronize(); t0 = time.perf_counter()

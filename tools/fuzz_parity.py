@@ -20,15 +20,13 @@ for seed in range(1000, 1000 + n_seeds):
         c = make_case(rng, k, cp, n, bw, mel, sparse=bool(rng.integers(0, 2)), homopolymer=False,
                       spacing=int(rng.integers(max(mel, 2), 14)))
         cases.append((mean, sigma) + c[2:])
+    before = T.TIE_LOG['tie']
     try:
-        T._compare_batch(rng, cases, k, cp, mel, bw, mean, sigma, exact=True)
+        T._compare_batch(rng, cases, k, cp, mel, bw, mean, sigma)
+        if T.TIE_LOG['tie'] > before:
+            ties += T.TIE_LOG['tie'] - before
+            print('seed', seed, 'k', k, 'cp', cp, 'mel', mel, 'bw', bw, 'structural tie(s):', T.TIE_LOG['tie'] - before)
     except AssertionError as e:
-        # a different path is acceptable only as an exact tie (equal max-product score under the oracle's posteriors)
-        try:
-            T._compare_batch(np.random.default_rng(seed), cases, k, cp, mel, bw, mean, sigma, exact=False)
-            ties += 1
-            print('seed', seed, 'k', k, 'cp', cp, 'mel', mel, 'bw', bw, 'tie (equal score path)')
-        except AssertionError as e2:
-            bad += 1
-            print('seed', seed, 'k', k, 'cp', cp, 'mel', mel, 'bw', bw, 'FAILED:', str(e2)[:300].replace('\n', ' '))
-print('%d seeds, %d failures, %d exact ties, %.0f s' % (n_seeds, bad, ties, time.time() - t0))
+        bad += 1
+        print('seed', seed, 'k', k, 'cp', cp, 'mel', mel, 'bw', bw, 'FAILED:', str(e)[:300].replace('\n', ' '))
+print('%d seeds, %d failures, %d structural ties among %d alignments, %.0f s' % (n_seeds, bad, ties, sum(T.TIE_LOG.values()), time.time() - t0))
