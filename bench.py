@@ -44,7 +44,8 @@ def parse_args():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--reads', type=int, default=1000, help='reads per GPU (weak scaling)')
     ap.add_argument('--bases', type=int, default=2000)
-    ap.add_argument('--genome', type=int, default=1_000_000)
+    ap.add_argument('--genome', type=int, default=4_600_000, help='synthetic genome length (E. coli-sized: configs[2])')
+    ap.add_argument('--no-consensus', action='store_true', help='skip the consensus-mode (configs[2]) step')
     ap.add_argument('--bandwidth', type=int, default=150)
     ap.add_argument('--cpu-sample', type=int, default=0, help='reads in the CPU sample (0 = one per host core)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -295,7 +296,7 @@ def workload_config(args, reads_per_gpu):
     return {'workload': 'configs[1]: estimate_snps independent=True, synthetic reads (~%d bases, ~%dk samples), '
                         'default config (bandwidth %d, min_event_length 2, wobbling, tweak), kmer_model.hdf5 6-mer'
                         % (args.bases, args.bases // 100, args.bandwidth),
-            'reads_per_gpu': reads_per_gpu, 'bandwidth': args.bandwidth,
+            'reads_per_gpu': reads_per_gpu, 'bandwidth': args.bandwidth, 'genome_bases': args.genome,
             'step': 'refine_alignment(plain) + estimate_log_likelihoods(wobbling) + chunk normalise + posterior',
             'l2': 'inputs larger than L2 (DP matrices of several GB per step)'}
 
@@ -397,6 +398,59 @@ def run_ours(args):
     n_check = cpu_sample_size(args, len(items)) if (world == 1 and not args.no_cpu_baseline) else 0
     gpu_events = batch_n.events()[0][:n_check] if n_check else []
     gpu_ll = batch_t.log_likelihoods()[0][:n_check] if n_check else []
+
+    # ---- consensus mode (configs[2]: estimate_snps independent=False, reads sharded over the ranks) ------------------
+    # Same resident reads, same DP work per step, but the per-position sums go over the reads of ALL ranks
+    # (estimator.py:226-231): timed region = refine -> estimate -> chunk normalise -> scatter-add into the consensus
+    # rows -> the exchange (reduce-scatter by genome slice + halo + all-gather over NCCL) -> posterior on the owned
+    # slice.  The overlap groups over all ranks' intervals are planned once (host, untimed), like `plan` above.
+    consensus = None
+    if not args.no_consensus:
+        pg = dist.group.WORLD if world > 1 else None
+        plan_c = est.plan_groups(intervals, genome, independent=False, process_group=pg)
+        ev_log = []
+
+        def consensus_step(collective='auto', log=None):
+            batch_n.refine(False, stream)
+            batch_t.estimate(True, stream)
+            return est.posterior_stage(batch_t, reverse, intervals, genome, independent=False, process_group=pg,
+                                       plan=plan_c, collective=collective, events=log)
+
+        for _ in range(2):
+            res_c = consensus_step()
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(args.steps):
+            log = {}
+            res_c = consensus_step(log=log)
+            ev_log.append(log)
+        c1.record(stream)
+        barrier()
+        c_ms = c0.elapsed_time(c1) / args.steps
+        x_ms = [sum(a.elapsed_time(b) for a, b in log.get('exchange', [])) for log in ev_log]
+        probs_c, cov_c = res_c[2], res_c[3]
+        # every rank must hold the same consensus; the two exchange variants must agree
+        check = torch.stack([probs_c.sum(), probs_c.square().sum(), cov_c.sum().double()])
+        hi_, lo_ = check.clone(), check.clone()
+        modes_diff = 0.0
+        if world > 1:
+            dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+            dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+            other = consensus_step(collective='allreduce')
+            modes_diff = float((other[2] - probs_c).abs().max().item())
+            barrier()
+        consensus = {
+            'ms_per_step': reduce_over_ranks(c_ms, 'max', dev),
+            'exchange_ms_per_step': reduce_over_ranks(float(np.mean(x_ms)) if x_ms else 0.0, 'max', dev),
+            'collective': ev_log[-1].get('mode', 'none (one rank)') if ev_log else None,
+            'bus_bytes_per_step': ev_log[-1].get('bus_bytes', 0.0) if ev_log else 0.0,
+            'positions': int(probs_c.shape[0]), 'groups': len(res_c[0]),
+            'mean_coverage': float(cov_c.double().mean().item()),
+            'ranks_identical': bool(torch.equal(hi_, lo_)),
+            'reduce_scatter_vs_allreduce_max_abs_diff': modes_diff,
+            'rows_sum_to_one_max_err': float((probs_c.sum(dim=1) - 1).abs().max().item()),
+        }
 
     # ---- software pipeline over consecutive batches (reported next to `value`, never instead of it) --------------
     # In a job of many batches the refine stage of batch k+1 does not depend on the estimate stage of batch k.  With
@@ -529,6 +583,13 @@ def run_ours(args):
                                   'rows_estimate': tt['rows'][0] / args.steps, 'no_snp': tt['no_snp'][0] / args.steps,
                                   'snp': tt['snp'][0] / args.steps},
             'cells_per_step_per_gpu': cells,
+            'consensus': None if consensus is None else dict(
+                consensus, value=samples_all / (consensus['ms_per_step'] * 1e-3), unit='samples/s',
+                bus_GBs=(consensus['bus_bytes_per_step'] / (consensus['exchange_ms_per_step'] * 1e-3) / 1e9
+                         if consensus['exchange_ms_per_step'] > 0 else None),
+                nvlink_peak_GBs_per_direction=900.0,
+                workload='configs[2] shape: estimate_snps independent=False, %d reads per GPU over a %.1f Mb '
+                         'synthetic genome; timed region includes the NCCL exchange' % (args.reads, args.genome / 1e6)),
             'pipelined': None if overlap_max is None else {
                 'value': samples_all / (overlap_max * 1e-3), 'unit': 'samples/s', 'ms_per_step': overlap_max,
                 'how': 'refine of the next batch on a second stream / workspace while the current batch is in its '

@@ -112,8 +112,10 @@ int nvb_batch_set_signal(nvb_batch *batch, const double *signal);
  * need more are processed in several waves of reads. */
 int nvb_batch_set_workspace_limit(nvb_batch *batch, int64_t bytes);
 /* run the kernels on `stream`; asynchronous with respect to the host except for wave planning.  The DP matrices live
- * in a workspace owned by the MODEL and shared by its batches (it grows to the largest wave seen and is freed with the
- * model): runs on batches of one model must not overlap in time -- issue them on one stream. */
+ * in workspaces owned by the MODEL, one per stream (each grows to the largest wave seen on its stream and is freed with
+ * the model): runs on one stream are ordered by the stream, runs on different streams use different workspaces, so
+ * batches of one model may be in flight on several streams at once.  The result getters (nvb_batch_get_*, event
+ * means, alignment table) read back on the stream of the batch's latest run and wait for that stream only. */
 int nvb_batch_refine(nvb_batch *batch, int model_transitions, void *stream);
 int nvb_batch_estimate(nvb_batch *batch, int model_wobbling, void *stream);
 /* results of the last run (blocking copies) */
@@ -172,6 +174,19 @@ int nvb_batch_chunk_values(nvb_batch *batch, const int32_t *reverse, double norm
  * for every read r with dest[r] >= 0 and status OK.  dest is a HOST array of n_reads row offsets. */
 int nvb_batch_scatter_add(nvb_batch *batch, const double *d_chunks, const int64_t *dest, double *d_acc,
                           int32_t *d_cov, void *stream);
+/* Consensus accumulator as ROWS of 5 doubles [sum A, sum C, sum G, sum T, coverage] (estimator.py:226-231): sums and
+ * coverage travel in one buffer, so the exchange between GPUs is one collective (reduce-scatter by genome slice, or
+ * all-reduce).  d_rows is a zero-initialised device buffer of (total rows, 5) doubles; dest as in
+ * nvb_batch_scatter_add. */
+int nvb_batch_scatter_add_rows(nvb_batch *batch, const double *d_chunks, const int64_t *dest, double *d_rows,
+                               void *stream);
+/* _compute_posterior (estimator.py:123-156) for the global rows [row_lo, row_hi) of the concatenated groups, from
+ * consensus rows that start at global row base_row (a rank's slice plus its k-1 halo rows); d_ref and d_group_off
+ * are indexed by global rows.  d_out_rows: (row_hi - row_lo, 5) doubles = [P(A), P(C), P(G), P(T), coverage].  Only
+ * enqueues the kernel on `stream`. */
+int nvb_posterior_rows_d(int device, const double *d_rows, int64_t base_row, int64_t row_lo, int64_t row_hi,
+                         const int8_t *d_ref, const int64_t *d_group_off, int32_t n_groups, int k, double snp_prior,
+                         double *d_out_rows, void *stream);
 /* _compute_posterior (estimator.py:123-156) over concatenated groups: d_ll double[total][4], d_ref int8[total]
  * (0..3, anything else = no base matches), group_off HOST int64[n_groups+1]; d_out double[total][4]. */
 int nvb_posterior(int device, const double *d_ll, const int8_t *d_ref, const int64_t *group_off,

@@ -81,6 +81,11 @@ SIGNATURES = {
                                               ctypes.c_void_p]),
     'nvb_batch_scatter_add': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_i64p, ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_void_p]),
+    'nvb_batch_scatter_add_rows': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_i64p, ctypes.c_void_p,
+                                                  ctypes.c_void_p]),
+    'nvb_posterior_rows_d': (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                            ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                            ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
     'nvb_posterior': (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, c_i64p, ctypes.c_int32,
                                      ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
     'nvb_posterior_d': (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,

@@ -18,6 +18,7 @@
 namespace {
 
 thread_local std::string g_err;
+thread_local int g_code = 0;  // code of the last failure on this thread (what the one-shot calls return)
 
 // Tuning / debugging switches: the environment is read ONCE, when the library is loaded; nvb_set_sweep_schedule
 // changes the schedule at run time (tests force both schedules through it).
@@ -40,6 +41,7 @@ int fail(int code, const char *fmt, ...) {
   vsnprintf(buf, sizeof buf, fmt, ap);
   va_end(ap);
   g_err = buf;
+  g_code = code;
   return code;
 }
 
@@ -108,8 +110,12 @@ struct DevBuf {
   size_t n = 0;         // elements requested
   size_t capacity = 0;  // bytes of the block
   int device = 0;
-  cudaError_t alloc(size_t count) {
+  // `owner`: the stream whose kernels may still be reading the current block.  A block that is outgrown goes back to
+  // the per-device cache, where any other stream may pick it up, so the owner is drained first (growth is rare: the
+  // workspaces only ever grow).
+  cudaError_t alloc(size_t count, cudaStream_t owner = nullptr, bool drain = false) {
     if (p && count * sizeof(T) <= capacity) { n = std::max(n, count); return cudaSuccess; }
+    if (p && drain) cudaStreamSynchronize(owner);
     release();
     cudaError_t e = pool_alloc((void **)&p, count * sizeof(T), &capacity, &device);
     if (e == cudaSuccess) n = count; else { p = nullptr; capacity = 0; }
@@ -132,14 +138,17 @@ cudaError_t upload(DevBuf<T> &buf, const T *src, size_t count, cudaStream_t st) 
 
 }  // namespace
 
-// DP workspace: owned by the model and shared by all of its batches (allocating and freeing several GB per batch
-// costs tens of milliseconds per call); it only ever grows and is released with the model.
+// DP workspace: owned by the model, ONE PER STREAM, shared by all batches of the model that run on that stream
+// (allocating and freeing several GB per batch costs tens of milliseconds per call); it only ever grows and is released
+// with the model.  Runs on the same stream are ordered by the stream, runs on different streams never share a
+// workspace, so batches of one model may be in flight on several streams at once.
 struct Workspace {
   DevBuf<double> pF, sF, dp;   // DP matrices: mantissa planes; path-search scratch rows
   DevBuf<int32_t> pX, sX;      // ... and exponent planes
   DevBuf<uint32_t> records;    // path search: one "new row record" bit per cell (path2.cu)
+  DevBuf<double> handoff;      // striped sweep: hand-off rows of band rows too wide for shared memory (rows4.cu)
   size_t bytes() const {
-    return pF.capacity + sF.capacity + dp.capacity + pX.capacity + sX.capacity + records.capacity;
+    return pF.capacity + sF.capacity + dp.capacity + pX.capacity + sX.capacity + records.capacity + handoff.capacity;
   }
 };
 
@@ -148,7 +157,18 @@ struct nvb_model {
   int sm_count = 148;
   ModelDev dev{};
   DevBuf<double> mean, ac, mc;
-  Workspace ws;
+  std::mutex ws_mutex;
+  std::map<cudaStream_t, Workspace> ws;  // std::map: references stay valid while other streams add theirs
+  Workspace &workspace(cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(ws_mutex);
+    return ws[st];
+  }
+  size_t workspace_bytes() {
+    std::lock_guard<std::mutex> lock(ws_mutex);
+    size_t total = 0;
+    for (auto &kv : ws) total += kv.second.bytes();
+    return total;
+  }
 };
 
 struct Wave { int b0, b1; int64_t cells; int maxw; };
@@ -181,6 +201,18 @@ struct nvb_batch {
   DevBuf<int64_t> d_mat_base, d_dp_base, d_rec_base;
   int64_t ws_limit = 0;
   int64_t launches = 0;
+  // Streams this batch has work on.  Results are read back on `run_stream` (the stream of the latest run); destroying
+  // the batch drains every stream that may still be using its buffers -- never the whole device.
+  cudaStream_t run_stream = nullptr;
+  std::vector<cudaStream_t> streams_used;
+  Workspace *last_ws = nullptr;  // workspace of the latest run (nvb_batch_debug_rows)
+  void touch(cudaStream_t st) {
+    run_stream = st;
+    if (std::find(streams_used.begin(), streams_used.end(), st) == streams_used.end()) streams_used.push_back(st);
+  }
+  void drain() {
+    for (cudaStream_t st : streams_used) cudaStreamSynchronize(st);
+  }
   // plan of the last run (see prepare_workspace)
   int plan_mode = -1;
   bool plan_dp = false;
@@ -380,9 +412,8 @@ int batch_init(nvb_batch *b, const nvb_reads *r) {
 
 // Forward + backward rows of one wave: the rotating wavefront (rows5.cu) when every read of the wave allows it, else
 // the pipelined stripes (rows4.cu).
-int run_sweep(nvb_batch *b, int mode, const Wave &w, cudaStream_t st) {
+int run_sweep(nvb_batch *b, Workspace &ws, int mode, const Wave &w, cudaStream_t st) {
   const ModelDev &M = b->model->dev;
-  Workspace &ws = b->model->ws;
   // Measured on B200 (profiles/r01d_sweep_schedules.txt): the rotating wavefront needs half the warp-steps but ~1.4x
   // the instructions per step and one warp per direction instead of two.  It wins when its warps (2 per read) fill one
   // resident wave of the GPU (16 warps per SM at its 128 registers) to 60 % or more; with fewer reads the striped
@@ -395,8 +426,11 @@ int run_sweep(nvb_batch *b, int mode, const Wave &w, cudaStream_t st) {
   for (int i = w.b0; i < w.b1 && rotate; i++) rotate = !b->no_rotation[i];
   if (rotate)
     return nvbk_sweep_rotate(M, b->dev, mode, w.b0, w.b1, b->d_mat_base.p, ws.pF.p, ws.pX.p, ws.sF.p, ws.sX.p, st);
+  // band rows too wide for the shared-memory hand-off rows of the striped sweep go through global scratch rows
+  const int64_t need = nvbk_sweep2_global_handoff_doubles(mode, w.b1 - w.b0, w.maxw, g_opt.sweep_warps);
+  if (need > 0 && ws.handoff.alloc((size_t)need, st, true) != cudaSuccess) { cudaGetLastError(); return -2; }
   return nvbk_sweep2(M, b->dev, mode, w.b0, w.b1, w.maxw, g_opt.sweep_warps, b->d_mat_base.p, ws.pF.p, ws.pX.p, ws.sF.p,
-                     ws.sX.p, st);
+                     ws.sX.p, need > 0 ? ws.handoff.p : nullptr, st);
 }
 
 int64_t matrix_cells(const nvb_batch *b, int i, int mode) {
@@ -417,7 +451,7 @@ int64_t record_words(const nvb_batch *b, int i, int mode) {
 }
 
 // Split the batch into waves of consecutive reads whose two DP matrices (+ path scratch) fit the workspace limit.
-int plan_waves(nvb_batch *b, int mode, bool need_dp, std::vector<Wave> &waves, std::vector<int64_t> &mat_base,
+int plan_waves(nvb_batch *b, const Workspace &ws, int mode, bool need_dp, std::vector<Wave> &waves, std::vector<int64_t> &mat_base,
                std::vector<int64_t> &dp_base, std::vector<int64_t> &rec_base, int64_t &max_cells, int64_t &max_dp,
                int64_t &max_rec) {
   int64_t limit = b->ws_limit;
@@ -430,7 +464,6 @@ int plan_waves(nvb_batch *b, int mode, bool need_dp, std::vector<Wave> &waves, s
       cells += matrix_cells(b, j, mode);
       if (need_dp) { dp += 2 * (int64_t)b->maxw[j]; rec += record_words(b, j, mode); }
     }
-    const Workspace &ws = b->model->ws;
     const bool fits = (size_t)cells * sizeof(double) <= ws.pF.capacity && (size_t)cells * sizeof(double) <= ws.sF.capacity &&
                       (size_t)cells * sizeof(int32_t) <= ws.pX.capacity && (size_t)cells * sizeof(int32_t) <= ws.sX.capacity &&
                       (size_t)dp * sizeof(double) <= ws.dp.capacity && (size_t)rec * sizeof(uint32_t) <= ws.records.capacity;
@@ -439,7 +472,7 @@ int plan_waves(nvb_batch *b, int mode, bool need_dp, std::vector<Wave> &waves, s
     } else {
       size_t free_b = 0, total_b = 0;
       CU(cudaMemGetInfo(&free_b, &total_b));
-      free_b += ws.bytes();
+      free_b += ws.bytes();  // what this stream's workspace already holds can be re-used
       limit = (int64_t)(free_b * 0.7);
     }
   }
@@ -473,7 +506,7 @@ int plan_waves(nvb_batch *b, int mode, bool need_dp, std::vector<Wave> &waves, s
   return NVB_OK;
 }
 
-int prepare_workspace(nvb_batch *b, int mode, bool need_dp, std::vector<Wave> &waves, cudaStream_t st) {
+int prepare_workspace(nvb_batch *b, Workspace &ws, int mode, bool need_dp, std::vector<Wave> &waves, cudaStream_t st) {
   std::vector<int64_t> mat_base, dp_base, rec_base;
   int64_t max_cells = 0, max_dp = 0, max_rec = 0;
   // The plan of the previous run is kept: repeating a run needs no host planning, no uploads and no synchronisation,
@@ -483,12 +516,12 @@ int prepare_workspace(nvb_batch *b, int mode, bool need_dp, std::vector<Wave> &w
     waves = b->plan_waves_cache;
     max_cells = b->plan_max[0]; max_dp = b->plan_max[1]; max_rec = b->plan_max[2];
   } else {
-    int rc = plan_waves(b, mode, need_dp, waves, mat_base, dp_base, rec_base, max_cells, max_dp, max_rec);
+    int rc = plan_waves(b, ws, mode, need_dp, waves, mat_base, dp_base, rec_base, max_cells, max_dp, max_rec);
     if (rc) return rc;
   }
-  if (b->model->ws.pF.alloc((size_t)max_cells) != cudaSuccess || b->model->ws.sF.alloc((size_t)max_cells) != cudaSuccess ||
-      b->model->ws.pX.alloc((size_t)max_cells) != cudaSuccess || b->model->ws.sX.alloc((size_t)max_cells) != cudaSuccess ||
-      b->model->ws.dp.alloc((size_t)max_dp) != cudaSuccess || b->model->ws.records.alloc((size_t)max_rec) != cudaSuccess) {
+  if (ws.pF.alloc((size_t)max_cells, st, true) != cudaSuccess || ws.sF.alloc((size_t)max_cells, st, true) != cudaSuccess ||
+      ws.pX.alloc((size_t)max_cells, st, true) != cudaSuccess || ws.sX.alloc((size_t)max_cells, st, true) != cudaSuccess ||
+      ws.dp.alloc((size_t)max_dp, st, true) != cudaSuccess || ws.records.alloc((size_t)max_rec, st, true) != cudaSuccess) {
     cudaGetLastError();
     return fail(NVB_ENOMEM, "cannot allocate %lld bytes of DP workspace",
                 (long long)(24 * max_cells + 8 * max_dp + 4 * max_rec));
@@ -510,6 +543,7 @@ int prepare_workspace(nvb_batch *b, int mode, bool need_dp, std::vector<Wave> &w
 extern "C" {
 
 nvb_batch *nvb_batch_create(nvb_model *model, const nvb_reads *reads) {
+  g_code = 0;
   if (!model || !reads) { fail(NVB_EINVAL, "nvb_batch_create: NULL argument"); return nullptr; }
   if (cudaSetDevice(model->device) != cudaSuccess) { fail(NVB_ECUDA, "cudaSetDevice failed"); return nullptr; }
   nvb_batch *b = new nvb_batch();
@@ -521,7 +555,7 @@ nvb_batch *nvb_batch_create(nvb_model *model, const nvb_reads *reads) {
 void nvb_batch_destroy(nvb_batch *batch) {
   if (!batch) return;
   cudaSetDevice(batch->model->device);
-  cudaDeviceSynchronize();  // its blocks go back to the cache: nothing may still be using them
+  batch->drain();  // its blocks go back to the cache: nothing on the streams it ran on may still be using them
   delete batch;
 }
 
@@ -536,7 +570,9 @@ int nvb_trim_memory(int device) {
 int nvb_batch_set_signal(nvb_batch *b, const double *signal) {
   if (!b || !signal) return fail(NVB_EINVAL, "nvb_batch_set_signal: NULL argument");
   CU(cudaSetDevice(b->model->device));
-  CU(cudaMemcpy(b->d_signal.p, signal, (size_t)b->total_sig * sizeof(double), cudaMemcpyHostToDevice));
+  b->drain();  // earlier runs may still be reading the old values
+  CU(cudaMemcpyAsync(b->d_signal.p, signal, (size_t)b->total_sig * sizeof(double), cudaMemcpyHostToDevice, b->run_stream));
+  CU(cudaStreamSynchronize(b->run_stream));
   return NVB_OK;
 }
 
@@ -552,21 +588,24 @@ int nvb_batch_refine(nvb_batch *b, int model_transitions, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int mode = model_transitions ? NVB_MODE_TRANS : NVB_MODE_PLAIN;
   std::vector<Wave> waves;
-  int rc = prepare_workspace(b, mode, true, waves, st);
+  Workspace &ws = b->model->workspace(st);
+  b->touch(st);
+  b->last_ws = &ws;
+  int rc = prepare_workspace(b, ws, mode, true, waves, st);
   if (rc) return rc;
-  CU(b->d_events.alloc((size_t)2 * b->total_ref));
+  CU(b->d_events.alloc((size_t)2 * b->total_ref, st, true));
   for (const Wave &w : waves) {
     {
       StageTimer t(b, 0, st);
-      const int src = run_sweep(b, mode, w, st);
+      const int src = run_sweep(b, ws, mode, w, st);
       if (src == -1) return fail(NVB_EINVAL, "min_event_length %d is not supported (maximum 6)", b->dev.mel);
-      if (src) return fail(NVB_ENOMEM, "band row of %d columns does not fit the sweep's shared-memory hand-off rows", w.maxw);
+      if (src) return fail(NVB_ENOMEM, "cannot allocate the hand-off rows of the sweep for a band row of %d columns", w.maxw);
     }
     if (!g_opt.skip_path) {  // debugging aid: keep the prefix plane for nvb_batch_debug_rows
       StageTimer t(b, 1, st);
-      nvbk_score(w.cells, b->model->ws.pF.p, b->model->ws.pX.p, b->model->ws.sF.p, b->model->ws.sX.p, st);
-      if (nvbk_path2(b->dev, mode, w.b0, w.b1, b->d_mat_base.p, b->model->ws.pF.p, b->model->ws.records.p, b->d_rec_base.p,
-                     b->model->ws.dp.p, b->d_dp_base.p, w.maxw, b->d_events.p, b->d_status.p, st))
+      nvbk_score(w.cells, ws.pF.p, ws.pX.p, ws.sF.p, ws.sX.p, st);
+      if (nvbk_path2(b->dev, mode, w.b0, w.b1, b->d_mat_base.p, ws.pF.p, ws.records.p, b->d_rec_base.p,
+                     ws.dp.p, b->d_dp_base.p, w.maxw, b->d_events.p, b->d_status.p, st))
         return fail(NVB_ECUDA, "path kernel: cannot reserve shared memory");
     }
     b->launches += 1;
@@ -585,28 +624,30 @@ int nvb_batch_estimate(nvb_batch *b, int model_wobbling, void *stream) {
   const int mode = model_wobbling ? NVB_MODE_WOBBLE : NVB_MODE_PLAIN;
   if (M.k + 2 > 32) return fail(NVB_EINVAL, "k = %d is too large for the SNP kernel (needs k+2 <= 32 lanes)", M.k);
   std::vector<Wave> waves;
-  int rc = prepare_workspace(b, mode, false, waves, st);
+  Workspace &ws = b->model->workspace(st);
+  b->touch(st);
+  b->last_ws = &ws;
+  int rc = prepare_workspace(b, ws, mode, false, waves, st);
   if (rc) return rc;
-  CU(b->d_ll.alloc((size_t)b->total_ref * M.alphabet));
+  CU(b->d_ll.alloc((size_t)b->total_ref * M.alphabet, st, true));
   nvbk_fill_status(b->dev, b->d_status.p, b->d_ll.p, M.alphabet, st);
   b->launches++;
   for (const Wave &w : waves) {
     {
       StageTimer t(b, 0, st);
-      const int src = run_sweep(b, mode, w, st);
+      const int src = run_sweep(b, ws, mode, w, st);
       if (src == -1) return fail(NVB_EINVAL, "min_event_length %d is not supported (maximum 6)", b->dev.mel);
-      if (src) return fail(NVB_ENOMEM, "band row of %d columns does not fit the sweep's shared-memory hand-off rows", w.maxw);
+      if (src) return fail(NVB_ENOMEM, "cannot allocate the hand-off rows of the sweep for a band row of %d columns", w.maxw);
     }
     {
       StageTimer t(b, 2, st);
-      nvbk_no_snp2(M, b->dev, w.b0, w.b1, b->d_mat_base.p, b->model->ws.pF.p, b->model->ws.pX.p, b->model->ws.sF.p, b->model->ws.sX.p, b->d_ll.p,
-                   st);
+      nvbk_no_snp2(M, b->dev, w.b0, w.b1, b->d_mat_base.p, ws.pF.p, ws.pX.p, ws.sF.p, ws.sX.p, b->d_ll.p, st);
     }
     int snp_rc;
     {
       StageTimer t(b, 3, st);
       snp_rc = nvbk_snp2(M, b->dev, model_wobbling, w.b0, w.b1, b->ref_off[w.b0], b->ref_off[w.b1],
-                         b->d_mat_base.p, b->model->ws.pF.p, b->model->ws.pX.p, b->model->ws.sF.p, b->model->ws.sX.p, b->d_ll.p, st);
+                         b->d_mat_base.p, ws.pF.p, ws.pX.p, ws.sF.p, ws.sX.p, b->d_ll.p, st);
     }
     if (snp_rc) return fail(NVB_EINVAL, "SNP kernel configuration not supported");
     b->launches += 3;
@@ -620,9 +661,10 @@ int nvb_batch_get_events(nvb_batch *b, int32_t *events, int32_t *status) {
   if (!b) return fail(NVB_EINVAL, "NULL batch");
   if (!b->have_events) return fail(NVB_ESTATE, "nvb_batch_get_events before nvb_batch_refine");
   CU(cudaSetDevice(b->model->device));
-  CU(cudaDeviceSynchronize());
-  if (events) CU(cudaMemcpy(events, b->d_events.p, (size_t)2 * b->total_ref * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  if (status) CU(cudaMemcpy(status, b->d_status.p, (size_t)b->n_reads * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  cudaStream_t st = b->run_stream;  // results are read back behind the run that produced them, on its stream
+  if (events) CU(cudaMemcpyAsync(events, b->d_events.p, (size_t)2 * b->total_ref * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (status) CU(cudaMemcpyAsync(status, b->d_status.p, (size_t)b->n_reads * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
   return NVB_OK;
 }
 
@@ -630,9 +672,10 @@ int nvb_batch_get_log_likelihoods(nvb_batch *b, double *out, int32_t *status) {
   if (!b) return fail(NVB_EINVAL, "NULL batch");
   if (!b->have_ll) return fail(NVB_ESTATE, "nvb_batch_get_log_likelihoods before nvb_batch_estimate");
   CU(cudaSetDevice(b->model->device));
-  CU(cudaDeviceSynchronize());
-  if (out) CU(cudaMemcpy(out, b->d_ll.p, (size_t)b->total_ref * b->model->dev.alphabet * sizeof(double), cudaMemcpyDeviceToHost));
-  if (status) CU(cudaMemcpy(status, b->d_status.p, (size_t)b->n_reads * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  cudaStream_t st = b->run_stream;
+  if (out) CU(cudaMemcpyAsync(out, b->d_ll.p, (size_t)b->total_ref * b->model->dev.alphabet * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (status) CU(cudaMemcpyAsync(status, b->d_status.p, (size_t)b->n_reads * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
   return NVB_OK;
 }
 
@@ -691,14 +734,16 @@ int nvb_batch_debug_rows(nvb_batch *b, int read, int plane, double *out_log, int
   if (!b || !out_log || read < 0 || read >= b->n_reads) return fail(NVB_EINVAL, "bad argument");
   if (n_cells != b->cells[read] && n_cells != 2 * b->cells[read] - b->w0[read] - b->wn[read])
     return fail(NVB_EINVAL, "read %d has %lld cells", read, (long long)b->cells[read]);
+  if (!b->last_ws) return fail(NVB_ESTATE, "nvb_batch_debug_rows before a run");
   CU(cudaSetDevice(b->model->device));
-  CU(cudaDeviceSynchronize());
+  CU(cudaStreamSynchronize(b->run_stream));
+  const Workspace &ws = *b->last_ws;
   int64_t base = 0;
   CU(cudaMemcpy(&base, b->d_mat_base.p + read, sizeof(int64_t), cudaMemcpyDeviceToHost));
   std::vector<double> f((size_t)n_cells);
   std::vector<int32_t> x((size_t)n_cells);
-  CU(cudaMemcpy(f.data(), (plane ? b->model->ws.sF.p : b->model->ws.pF.p) + base, (size_t)n_cells * sizeof(double), cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(x.data(), (plane ? b->model->ws.sX.p : b->model->ws.pX.p) + base, (size_t)n_cells * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(f.data(), (plane ? ws.sF.p : ws.pF.p) + base, (size_t)n_cells * sizeof(double), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(x.data(), (plane ? ws.sX.p : ws.pX.p) + base, (size_t)n_cells * sizeof(int32_t), cudaMemcpyDeviceToHost));
   for (int64_t i = 0; i < n_cells; i++)
     out_log[i] = f[i] > 0.0 ? log(f[i]) + x[i] * 0.6931471805599453 : -INFINITY;
   return NVB_OK;
@@ -713,7 +758,7 @@ int nvb_batch_enable_timing(nvb_batch *b, int on) {
 int nvb_batch_get_timing(nvb_batch *b, double ms[NVB_N_STAGES], int64_t launches[NVB_N_STAGES]) {
   if (!b || !ms || !launches) return fail(NVB_EINVAL, "NULL argument");
   CU(cudaSetDevice(b->model->device));
-  CU(cudaDeviceSynchronize());
+  b->drain();
   for (int i = 0; i < NVB_N_STAGES; i++) { ms[i] = 0; launches[i] = 0; }
   for (auto &t : b->timed) {
     float x = 0;
@@ -751,7 +796,7 @@ int nvb_measure_fp64_fma_rate(int device, double *fma_per_second) {
 int nvb_refine_alignment_batch(nvb_model *model, const nvb_reads *reads, int model_transitions, int32_t *events,
                                int32_t *status) {
   nvb_batch *b = nvb_batch_create(model, reads);
-  if (!b) return NVB_EINVAL;
+  if (!b) return g_code ? g_code : NVB_EINVAL;  // the code nvb_batch_create failed with (EINVAL / ECUDA / ENOMEM)
   int rc = nvb_batch_refine(b, model_transitions, nullptr);
   if (!rc) rc = nvb_batch_get_events(b, events, status);
   nvb_batch_destroy(b);
@@ -761,7 +806,7 @@ int nvb_refine_alignment_batch(nvb_model *model, const nvb_reads *reads, int mod
 int nvb_estimate_log_likelihoods_batch(nvb_model *model, const nvb_reads *reads, int model_wobbling, double *out,
                                        int32_t *status) {
   nvb_batch *b = nvb_batch_create(model, reads);
-  if (!b) return NVB_EINVAL;
+  if (!b) return g_code ? g_code : NVB_EINVAL;
   int rc = nvb_batch_estimate(b, model_wobbling, nullptr);
   if (!rc) rc = nvb_batch_get_log_likelihoods(b, out, status);
   nvb_batch_destroy(b);
@@ -801,14 +846,16 @@ int nvb_batch_get_alignment_table(nvb_batch *b, const int64_t *start_in_signal, 
   std::copy(start_in_signal, start_in_signal + n, meta.begin());
   std::copy(ref_start, ref_start + n, meta.begin() + n);
   std::copy(ref_end, ref_end + n, meta.begin() + 2 * n);
-  CU(upload(d_meta, meta.data(), meta.size(), 0));
-  CU(upload(d_rev, reverse, n, 0));
+  cudaStream_t st = b->run_stream;  // behind the refine that produced the events
+  CU(upload(d_meta, meta.data(), meta.size(), st));
+  CU(upload(d_rev, reverse, n, st));
   CU(d_out.alloc((size_t)3 * b->total_ref));
   nvbk_alignment_table(b->dev, b->d_events.p, b->d_status.p, d_meta.p, d_meta.p + n, d_meta.p + 2 * n, d_rev.p,
-                       b->total_ref, d_out.p, 0);
+                       b->total_ref, d_out.p, st);
   b->launches++;
   CU(cudaGetLastError());
-  CU(cudaMemcpy(out, d_out.p, (size_t)3 * b->total_ref * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpyAsync(out, d_out.p, (size_t)3 * b->total_ref * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));  // the temporaries go back to the block cache on return
   return NVB_OK;
 }
 
@@ -817,11 +864,13 @@ int nvb_batch_event_means(nvb_batch *b, double *out) {
   if (!b->have_events) return fail(NVB_ESTATE, "event means requested before nvb_batch_refine");
   CU(cudaSetDevice(b->model->device));
   DevBuf<double> d_out;
+  cudaStream_t st = b->run_stream;  // behind the refine that produced the events
   CU(d_out.alloc((size_t)b->total_ref));
-  nvbk_event_means(b->dev, b->d_events.p, b->d_status.p, b->total_ref, d_out.p, 0);
+  nvbk_event_means(b->dev, b->d_events.p, b->d_status.p, b->total_ref, d_out.p, st);
   b->launches++;
   CU(cudaGetLastError());
-  CU(cudaMemcpy(out, d_out.p, (size_t)b->total_ref * sizeof(double), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpyAsync(out, d_out.p, (size_t)b->total_ref * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
   return NVB_OK;
 }
 
@@ -839,6 +888,7 @@ int nvb_batch_apply_splines(nvb_batch *b, const double *knots, const double *coe
   }
   CU(cudaSetDevice(b->model->device));
   cudaStream_t st = (cudaStream_t)stream;
+  b->touch(st);
   DevBuf<double> d_knots, d_coefs;
   DevBuf<int64_t> d_off;
   CU(upload(d_knots, knots, (size_t)total, st));
@@ -854,8 +904,8 @@ int nvb_batch_apply_splines(nvb_batch *b, const double *knots, const double *coe
 int nvb_batch_get_signal(nvb_batch *b, double *out) {
   if (!b || !out) return fail(NVB_EINVAL, "NULL argument");
   CU(cudaSetDevice(b->model->device));
-  CU(cudaDeviceSynchronize());
-  CU(cudaMemcpy(out, b->d_signal.p, (size_t)b->total_sig * sizeof(double), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpyAsync(out, b->d_signal.p, (size_t)b->total_sig * sizeof(double), cudaMemcpyDeviceToHost, b->run_stream));
+  CU(cudaStreamSynchronize(b->run_stream));
   return NVB_OK;
 }
 
@@ -866,6 +916,7 @@ int nvb_batch_chunk_values(nvb_batch *b, const int32_t *reverse, double normaliz
   if (b->model->dev.alphabet != 4) return fail(NVB_EINVAL, "chunk values need alphabet_size == 4");
   CU(cudaSetDevice(b->model->device));
   cudaStream_t st = (cudaStream_t)stream;
+  b->touch(st);
   const size_t n = (size_t)b->n_reads;
   if (b->h_rev.size() != n || !std::equal(reverse, reverse + n, b->h_rev.begin())) {
     CU(cudaStreamSynchronize(st));  // an earlier launch may still read the old values
@@ -884,6 +935,7 @@ int nvb_batch_scatter_add(nvb_batch *b, const double *d_chunks, const int64_t *d
   if (!b || !d_chunks || !dest || !d_acc || !d_cov) return fail(NVB_EINVAL, "NULL argument");
   CU(cudaSetDevice(b->model->device));
   cudaStream_t st = (cudaStream_t)stream;
+  b->touch(st);
   const size_t n = (size_t)b->n_reads;
   if (b->h_dest.size() != n || !std::equal(dest, dest + n, b->h_dest.begin())) {
     CU(cudaStreamSynchronize(st));
@@ -893,6 +945,37 @@ int nvb_batch_scatter_add(nvb_batch *b, const double *d_chunks, const int64_t *d
   }
   nvbk_scatter_add(b->dev, d_chunks, b->d_dest.p, b->d_status.p, b->total_ref, d_acc, d_cov, st);
   b->launches++;
+  CU(cudaGetLastError());
+  return NVB_OK;
+}
+
+int nvb_batch_scatter_add_rows(nvb_batch *b, const double *d_chunks, const int64_t *dest, double *d_rows, void *stream) {
+  if (!b || !d_chunks || !dest || !d_rows) return fail(NVB_EINVAL, "NULL argument");
+  CU(cudaSetDevice(b->model->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  b->touch(st);
+  const size_t n = (size_t)b->n_reads;
+  if (b->h_dest.size() != n || !std::equal(dest, dest + n, b->h_dest.begin())) {
+    CU(cudaStreamSynchronize(st));
+    b->h_dest.assign(dest, dest + n);
+    CU(upload(b->d_dest, b->h_dest.data(), n, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  nvbk_scatter_add_rows(b->dev, d_chunks, b->d_dest.p, b->d_status.p, b->total_ref, d_rows, st);
+  b->launches++;
+  CU(cudaGetLastError());
+  return NVB_OK;
+}
+
+int nvb_posterior_rows_d(int device, const double *d_rows, int64_t base_row, int64_t row_lo, int64_t row_hi,
+                         const int8_t *d_ref, const int64_t *d_group_off, int32_t n_groups, int k, double snp_prior,
+                         double *d_out_rows, void *stream) {
+  if (!d_rows || !d_ref || !d_group_off || !d_out_rows || n_groups < 0 || row_hi < row_lo || base_row > row_lo)
+    return fail(NVB_EINVAL, "bad argument");
+  if (nvb_device_count() <= device) return fail(NVB_ECUDA, "CUDA device %d not available (no CPU fallback)", device);
+  CU(cudaSetDevice(device));
+  nvbk_posterior_rows(d_rows, base_row, row_lo, row_hi, d_ref, d_group_off, n_groups, k, snp_prior, d_out_rows,
+                      (cudaStream_t)stream);
   CU(cudaGetLastError());
   return NVB_OK;
 }

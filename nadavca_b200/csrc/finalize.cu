@@ -155,11 +155,27 @@ __global__ void scatter_add_kernel(BatchDev B, const double *chunks, const int64
   atomicAdd(cov + p, 1);
 }
 
-// _compute_posterior: window [max(0,i-k+1), min(i+k,L)) inside the position's group, same accumulation order.
-__global__ void posterior_kernel(const double *ll, const int8_t *ref, const int64_t *group_off, int n_groups,
-                                 int64_t total, int k, double snp_prior, double *out) {
+// Consensus accumulator as ROWS of 5 doubles [A, C, G, T, coverage]: the sums of estimator.py:226-231 and the coverage
+// count of estimator.py:229-230 in one buffer, so that the exchange between GPUs is ONE collective (coverage counts
+// are small integers, exact in a double).
+__global__ void scatter_add_rows_kernel(BatchDev B, const double *chunks, const int64_t *dest, const int32_t *status,
+                                        int64_t total, double *rows) {
   int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (g >= total) return;
+  const int b = find_read(B, g);
+  if (dest[b] < 0 || status[b] != 0) return;
+  const int64_t p = dest[b] + (g - B.ref_off[b]);
+#pragma unroll
+  for (int j = 0; j < 4; j++) atomicAdd(rows + p * 5 + j, chunks[g * 4 + j]);
+  atomicAdd(rows + p * 5 + 4, 1.0);
+}
+
+// _compute_posterior (estimator.py:131-156) at global row g: window [max(0,i-k+1), min(i+k,L)) inside the position's
+// group, same accumulation order as the reference.  `ll` holds rows of `ld` doubles starting at global row `base`
+// (ld = 4, base = 0: a plain (total, 4) matrix; ld = 5: a slice of the consensus rows with its k-1 halo rows).
+__device__ __forceinline__ void posterior_at(const double *ll, int ld, int64_t base, const int8_t *ref,
+                                             const int64_t *group_off, int n_groups, int64_t g, int k, double snp_prior,
+                                             double pr_out[4]) {
   int lo = 0, hi = n_groups;
   while (hi - lo > 1) {
     int mid = (lo + hi) >> 1;
@@ -168,9 +184,10 @@ __global__ void posterior_kernel(const double *ll, const int8_t *ref, const int6
   const int64_t gs = group_off[lo], ge = group_off[lo + 1];
   const int64_t i = g - gs, L = ge - gs;
   const int64_t cs = max((int64_t)0, i - k + 1), ce = min(i + k, L);
+  const double *row0 = ll + (gs - base) * ld;  // row of the group's first position
   double mx = nvb_neg_inf();
   for (int64_t i2 = cs; i2 < ce; i2++)
-    for (int j = 0; j < 4; j++) mx = fmax(mx, ll[(gs + i2) * 4 + j]);
+    for (int j = 0; j < 4; j++) mx = fmax(mx, row0[i2 * ld + j]);
   // _corrected_priors (estimator.py:123-129)
   const double c = 3.0;
   const double p1 = 1 - snp_prior, p2 = snp_prior / c;
@@ -180,14 +197,14 @@ __global__ void posterior_kernel(const double *ll, const int8_t *ref, const int6
   const int rb = ref[g];
   for (int j = 0; j < 4; j++) {
     const double prior = (j != rb) ? snp_h : nonsnp_h;
-    double v = exp(ll[g * 4 + j] - mx) * prior;
+    double v = exp(row0[i * ld + j] - mx) * prior;
     if (j == rb) {
       for (int64_t i2 = cs; i2 < ce; i2++) {
         if (i2 == i) continue;
         const int rb2 = ref[gs + i2];
         for (int j2 = 0; j2 < 4; j2++) {
           if (j2 == rb2) continue;
-          v += exp(ll[(gs + i2) * 4 + j2] - mx) * snp_h;
+          v += exp(row0[i2 * ld + j2] - mx) * snp_h;
         }
       }
     }
@@ -195,7 +212,30 @@ __global__ void posterior_kernel(const double *ll, const int8_t *ref, const int6
   }
   double sum = 0.0;  // Python's builtin sum() starts from int 0
   for (int j = 0; j < 4; j++) sum += pr[j];
-  for (int j = 0; j < 4; j++) out[g * 4 + j] = pr[j] / sum;
+  for (int j = 0; j < 4; j++) pr_out[j] = pr[j] / sum;
+}
+
+__global__ void posterior_kernel(const double *ll, const int8_t *ref, const int64_t *group_off, int n_groups,
+                                 int64_t total, int k, double snp_prior, double *out) {
+  int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  double pr[4];
+  posterior_at(ll, 4, 0, ref, group_off, n_groups, g, k, snp_prior, pr);
+  for (int j = 0; j < 4; j++) out[g * 4 + j] = pr[j];
+}
+
+// Posterior of the global rows [row_lo, row_hi) from consensus rows of 5 doubles that start at global row `base`
+// (base <= row_lo - (k-1) unless row_lo opens a group): out rows of 5 = [P(A), P(C), P(G), P(T), coverage].
+__global__ void posterior_rows_kernel(const double *rows, int64_t base, int64_t row_lo, int64_t row_hi,
+                                      const int8_t *ref, const int64_t *group_off, int n_groups, int k, double snp_prior,
+                                      double *out) {
+  int64_t g = row_lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= row_hi) return;
+  double pr[4];
+  posterior_at(rows, 5, base, ref, group_off, n_groups, g, k, snp_prior, pr);
+  double *o = out + (g - row_lo) * 5;
+  for (int j = 0; j < 4; j++) o[j] = pr[j];
+  o[4] = rows[(g - base) * 5 + 4];
 }
 
 __global__ void fill_status_kernel(BatchDev B, int32_t *status, double *ll, int alphabet) {
@@ -248,6 +288,19 @@ void nvbk_posterior(const double *d_ll, const int8_t *d_ref, const int64_t *d_gr
   if (total > 0)
     posterior_kernel<<<blocks_for(total), 256, 0, st>>>(d_ll, d_ref, d_group_off, n_groups, total, k, snp_prior,
                                                         d_out);
+}
+
+void nvbk_scatter_add_rows(const BatchDev &B, const double *d_chunks, const int64_t *d_dest, const int32_t *d_status,
+                           int64_t total, double *d_rows, cudaStream_t st) {
+  if (total > 0) scatter_add_rows_kernel<<<blocks_for(total), 256, 0, st>>>(B, d_chunks, d_dest, d_status, total, d_rows);
+}
+
+void nvbk_posterior_rows(const double *d_rows, int64_t base, int64_t row_lo, int64_t row_hi, const int8_t *d_ref,
+                         const int64_t *d_group_off, int n_groups, int k, double snp_prior, double *d_out,
+                         cudaStream_t st) {
+  if (row_hi > row_lo)
+    posterior_rows_kernel<<<blocks_for(row_hi - row_lo), 256, 0, st>>>(d_rows, base, row_lo, row_hi, d_ref, d_group_off,
+                                                                     n_groups, k, snp_prior, d_out);
 }
 
 void nvbk_fill_status(const BatchDev &B, int32_t *d_status, double *d_ll, int alphabet, cudaStream_t st) {

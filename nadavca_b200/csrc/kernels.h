@@ -9,8 +9,12 @@ void nvbk_expected_signal(const ModelDev &M, const BatchDev &B, int64_t total, d
 // rows4.cu: forward + backward banded rows for reads [b0,b1): one CTA per (read, direction), stripes pipelined over
 // its warps; rows are stored as a mantissa plane (double) and an exponent plane (int32).  wave_maxw = widest band
 // row of the wave.  Returns -1 for an unsupported min_event_length, -2 when the hand-off rows do not fit shared memory.
+// g_handoff: global scratch for the hand-off rows of band rows too wide for shared memory (size from
+// nvbk_sweep2_global_handoff_doubles, 0 = not needed).
+int64_t nvbk_sweep2_global_handoff_doubles(int mode, int n_reads, int wave_maxw, int force_warps);
 int nvbk_sweep2(const ModelDev &M, const BatchDev &B, int mode, int b0, int b1, int wave_maxw, int force_warps,
-                const int64_t *d_mat_base, double *pF, int32_t *pX, double *sF, int32_t *sX, cudaStream_t st);
+                const int64_t *d_mat_base, double *pF, int32_t *pX, double *sF, int32_t *sX, double *g_handoff,
+                cudaStream_t st);
 // rows5.cu: the same rows with one continuously rotating wavefront per (read, direction); for reads whose bands allow
 // it (band.cu flags the others).  Returns -1 for an unsupported min_event_length.
 int nvbk_sweep_rotate(const ModelDev &M, const BatchDev &B, int mode, int b0, int b1, const int64_t *d_mat_base,
@@ -47,6 +51,11 @@ void nvbk_scatter_add(const BatchDev &B, const double *d_chunks, const int64_t *
                       int64_t total, double *d_acc, int32_t *d_cov, cudaStream_t st);
 void nvbk_posterior(const double *d_ll, const int8_t *d_ref, const int64_t *d_group_off, int n_groups,
                     int64_t total, int k, double snp_prior, double *d_out, cudaStream_t st);
+void nvbk_scatter_add_rows(const BatchDev &B, const double *d_chunks, const int64_t *d_dest, const int32_t *d_status,
+                           int64_t total, double *d_rows, cudaStream_t st);
+void nvbk_posterior_rows(const double *d_rows, int64_t base, int64_t row_lo, int64_t row_hi, const int8_t *d_ref,
+                         const int64_t *d_group_off, int n_groups, int k, double snp_prior, double *d_out,
+                         cudaStream_t st);
 void nvbk_fill_status(const BatchDev &B, int32_t *d_status, double *d_ll, int alphabet, cudaStream_t st);
 
 // microbench.cu

@@ -257,7 +257,7 @@ __device__ __forceinline__ void sweep_stripes(const ModelDev &M, const ReadView 
 template <int MEL, int MODE>
 __global__ void __launch_bounds__(224, 4) sweep4_kernel(ModelDev M, BatchDev B, int b0, int n_items, int NW, int width,
                                                      const int64_t *mat_base, double *pF, int32_t *pX, double *sF,
-                                                     int32_t *sX) {
+                                                     int32_t *sX, double *g_handoff) {
   extern __shared__ unsigned long long smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x;  // (read, direction)
@@ -268,10 +268,20 @@ __global__ void __launch_bounds__(224, 4) sweep4_kernel(ModelDev M, BatchDev B, 
   H.nb = NW + 1;
   H.width = width;
   H.word = smem_raw;                                   // [nb] (padded to 8 words)
-  H.f = reinterpret_cast<double *>(smem_raw + 8);      // nb <= 8
-  H.e = reinterpret_cast<int32_t *>(H.f + (size_t)H.nb * width);
+  unsigned char *tiles;
+  if (g_handoff == nullptr) {
+    H.f = reinterpret_cast<double *>(smem_raw + 8);    // nb <= 8
+    H.e = reinterpret_cast<int32_t *>(H.f + (size_t)H.nb * width);
+    tiles = reinterpret_cast<unsigned char *>(H.e + (size_t)H.nb * width);
+  } else {
+    // band rows too wide for shared memory: the hand-off rows of this (read, direction) live in global scratch
+    // (2 * nb * width doubles per item).  Producer and consumer are warps of the same CTA, so the block-scope fence
+    // in front of the ready word and the volatile reads behind it order the accesses exactly as in shared memory.
+    H.f = g_handoff + (size_t)item * 2 * H.nb * width;
+    H.e = reinterpret_cast<int32_t *>(H.f + (size_t)H.nb * width);
+    tiles = reinterpret_cast<unsigned char *>(smem_raw + 8);
+  }
   // per-warp store tiles behind the hand-off rows (B rows, and A rows for the transition sweep)
-  unsigned char *tiles = reinterpret_cast<unsigned char *>(H.e + (size_t)H.nb * width);
   auto make_tile = [&](int index) {
     unsigned char *p = tiles + (size_t)index * kTileBytes;
     StoreTile t;
@@ -326,53 +336,78 @@ __global__ void __launch_bounds__(128) no_snp2_kernel(ModelDev M, BatchDev B, in
 
 template <int MEL, int MODE>
 int launch_mode(const ModelDev &M, const BatchDev &B, int b0, int n_items, int NW, int width, size_t smem,
-                const int64_t *mb, double *pF, int32_t *pX, double *sF, int32_t *sX, cudaStream_t st) {
+                const int64_t *mb, double *pF, int32_t *pX, double *sF, int32_t *sX, double *gh, cudaStream_t st) {
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(sweep4_kernel<MEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return -2;
-  sweep4_kernel<MEL, MODE><<<n_items, NW * NVB_WARP, smem, st>>>(M, B, b0, n_items, NW, width, mb, pF, pX, sF, sX);
+  sweep4_kernel<MEL, MODE><<<n_items, NW * NVB_WARP, smem, st>>>(M, B, b0, n_items, NW, width, mb, pF, pX, sF, sX, gh);
   return 0;
 }
 
 template <int MEL>
 int launch_sweep4(const ModelDev &M, const BatchDev &B, int mode, int b0, int n_items, int NW, int width, size_t smem,
-                  const int64_t *mb, double *pF, int32_t *pX, double *sF, int32_t *sX, cudaStream_t st) {
+                  const int64_t *mb, double *pF, int32_t *pX, double *sF, int32_t *sX, double *gh, cudaStream_t st) {
   switch (mode) {
-    case NVB_MODE_PLAIN: return launch_mode<MEL, NVB_MODE_PLAIN>(M, B, b0, n_items, NW, width, smem, mb, pF, pX, sF, sX, st);
-    case NVB_MODE_TRANS: return launch_mode<MEL, NVB_MODE_TRANS>(M, B, b0, n_items, NW, width, smem, mb, pF, pX, sF, sX, st);
-    default: return launch_mode<MEL, NVB_MODE_WOBBLE>(M, B, b0, n_items, NW, width, smem, mb, pF, pX, sF, sX, st);
+    case NVB_MODE_PLAIN: return launch_mode<MEL, NVB_MODE_PLAIN>(M, B, b0, n_items, NW, width, smem, mb, pF, pX, sF, sX, gh, st);
+    case NVB_MODE_TRANS: return launch_mode<MEL, NVB_MODE_TRANS>(M, B, b0, n_items, NW, width, smem, mb, pF, pX, sF, sX, gh, st);
+    default: return launch_mode<MEL, NVB_MODE_WOBBLE>(M, B, b0, n_items, NW, width, smem, mb, pF, pX, sF, sX, gh, st);
   }
 }
 
-}  // namespace
+// Launch geometry of the striped sweep for a wave whose widest band row has wave_maxw columns.
+struct SweepPlan {
+  int NW, width;
+  size_t smem;
+  bool global_handoff;
+};
 
-// wave_maxw: widest band row among the reads [b0, b1).  Returns -1 for an unsupported min_event_length, -2 when the
-// shared-memory reservation fails.
-int nvbk_sweep2(const ModelDev &M, const BatchDev &B, int mode, int b0, int b1, int wave_maxw, int force_warps,
-                const int64_t *d_mat_base, double *pF, int32_t *pX, double *sF, int32_t *sX, cudaStream_t st) {
-  const int n_items = 2 * (b1 - b0);
-  if (n_items <= 0) return 0;
+SweepPlan plan_sweep(int mode, int wave_maxw, int force_warps) {
+  SweepPlan p;
   // warps per (read, direction): a stripe lasts ~W + 12*31 steps, a new one can start every ~11*31 steps
-  const int width = (wave_maxw + 1) & ~1;  // keeps the int32 plane 8-byte aligned
+  p.width = (wave_maxw + 1) & ~1;  // keeps the int32 plane 8-byte aligned
   int NW = (wave_maxw + 12 * PAIRS + 11 * PAIRS - 1) / (11 * PAIRS);
   NW = NW < 1 ? 1 : (NW > 7 ? 7 : NW);
   if (force_warps > 0) NW = force_warps > 7 ? 7 : force_warps;  // experiments (NVB_SWEEP_WARPS, read at load)
   const int tiles_per_warp = (mode == NVB_MODE_TRANS) ? 2 : 1;
-  auto bytes = [&](int nw) {
-    return (size_t)64 + (size_t)(nw + 1) * width * (sizeof(double) + sizeof(int32_t)) +
-           (size_t)tiles_per_warp * nw * kTileBytes;
-  };
-  while (NW > 1 && bytes(NW) > 200 * 1024) NW--;
-  if (bytes(NW) > 200 * 1024) return -2;
-  const size_t smem = bytes(NW);
+  auto tile_bytes = [&](int nw) { return (size_t)64 + (size_t)tiles_per_warp * nw * kTileBytes; };
+  auto bytes = [&](int nw) { return tile_bytes(nw) + (size_t)(nw + 1) * p.width * (sizeof(double) + sizeof(int32_t)); };
+  const size_t limit = 200 * 1024;
+  p.global_handoff = bytes(1) > limit;  // not even two hand-off rows fit (band rows beyond ~8.5k columns)
+  if (!p.global_handoff)
+    while (NW > 1 && bytes(NW) > limit) NW--;
+  p.NW = NW;
+  p.smem = p.global_handoff ? tile_bytes(NW) : bytes(NW);
+  return p;
+}
+
+}  // namespace
+
+// Doubles of global scratch the striped sweep needs for its hand-off rows (0 when they fit shared memory).
+int64_t nvbk_sweep2_global_handoff_doubles(int mode, int n_reads, int wave_maxw, int force_warps) {
+  const SweepPlan p = plan_sweep(mode, wave_maxw, force_warps);
+  return p.global_handoff ? (int64_t)2 * n_reads * 2 * (p.NW + 1) * p.width : 0;
+}
+
+// wave_maxw: widest band row among the reads [b0, b1).  Returns -1 for an unsupported min_event_length, -2 when the
+// shared-memory reservation fails.
+int nvbk_sweep2(const ModelDev &M, const BatchDev &B, int mode, int b0, int b1, int wave_maxw, int force_warps,
+                const int64_t *d_mat_base, double *pF, int32_t *pX, double *sF, int32_t *sX, double *g_handoff,
+                cudaStream_t st) {
+  const int n_items = 2 * (b1 - b0);
+  if (n_items <= 0) return 0;
+  const SweepPlan p = plan_sweep(mode, wave_maxw, force_warps);
+  if (p.global_handoff && g_handoff == nullptr) return -2;
+  double *gh = p.global_handoff ? g_handoff : nullptr;
+  const int NW = p.NW, width = p.width;
+  const size_t smem = p.smem;
   switch (B.mel) {
-    case 0: return launch_sweep4<0>(M, B, mode, b0, n_items, NW, width, smem, d_mat_base, pF, pX, sF, sX, st);
-    case 1: return launch_sweep4<1>(M, B, mode, b0, n_items, NW, width, smem, d_mat_base, pF, pX, sF, sX, st);
-    case 2: return launch_sweep4<2>(M, B, mode, b0, n_items, NW, width, smem, d_mat_base, pF, pX, sF, sX, st);
-    case 3: return launch_sweep4<3>(M, B, mode, b0, n_items, NW, width, smem, d_mat_base, pF, pX, sF, sX, st);
-    case 4: return launch_sweep4<4>(M, B, mode, b0, n_items, NW, width, smem, d_mat_base, pF, pX, sF, sX, st);
-    case 5: return launch_sweep4<5>(M, B, mode, b0, n_items, NW, width, smem, d_mat_base, pF, pX, sF, sX, st);
-    case 6: return launch_sweep4<6>(M, B, mode, b0, n_items, NW, width, smem, d_mat_base, pF, pX, sF, sX, st);
+    case 0: return launch_sweep4<0>(M, B, mode, b0, n_items, NW, width, smem, d_mat_base, pF, pX, sF, sX, gh, st);
+    case 1: return launch_sweep4<1>(M, B, mode, b0, n_items, NW, width, smem, d_mat_base, pF, pX, sF, sX, gh, st);
+    case 2: return launch_sweep4<2>(M, B, mode, b0, n_items, NW, width, smem, d_mat_base, pF, pX, sF, sX, gh, st);
+    case 3: return launch_sweep4<3>(M, B, mode, b0, n_items, NW, width, smem, d_mat_base, pF, pX, sF, sX, gh, st);
+    case 4: return launch_sweep4<4>(M, B, mode, b0, n_items, NW, width, smem, d_mat_base, pF, pX, sF, sX, gh, st);
+    case 5: return launch_sweep4<5>(M, B, mode, b0, n_items, NW, width, smem, d_mat_base, pF, pX, sF, sX, gh, st);
+    case 6: return launch_sweep4<6>(M, B, mode, b0, n_items, NW, width, smem, d_mat_base, pF, pX, sF, sX, gh, st);
     default: return -1;
   }
 }

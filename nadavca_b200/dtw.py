@@ -259,6 +259,13 @@ class Batch:
                                                    _cabi.ptr(d, ctypes.c_int64), ctypes.c_void_p(d_acc),
                                                    ctypes.c_void_p(d_cov), _stream(stream)), 'nvb_batch_scatter_add')
 
+    def scatter_add_rows(self, d_chunks, dest, d_rows, stream=None):
+        """Add the chunks into consensus rows of 5 doubles [A, C, G, T, coverage] (one buffer, one collective)."""
+        d = _cabi.as_array(dest, np.int64)
+        _cabi.check(self.lib.nvb_batch_scatter_add_rows(self.handle, ctypes.c_void_p(d_chunks),
+                                                        _cabi.ptr(d, ctypes.c_int64), ctypes.c_void_p(d_rows),
+                                                        _stream(stream)), 'nvb_batch_scatter_add_rows')
+
     def debug_rows(self, read, plane, transitions=False):
         """Stored DP rows of one read after estimate() as log-probabilities (plane 0 prefix, 1 suffix)."""
         bs, be = self.bands()[read]
@@ -331,6 +338,17 @@ def posterior_resident(device, d_ll, d_ref, d_group_off, n_groups, total, k, snp
     _cabi.check(lib.nvb_posterior_d(int(device), ctypes.c_void_p(d_ll), ctypes.c_void_p(d_ref),
                                     ctypes.c_void_p(d_group_off), int(n_groups), int(total), int(k), float(snp_prior),
                                     ctypes.c_void_p(d_out), _stream(stream)), 'nvb_posterior_d')
+
+
+def posterior_rows(device, d_rows, base_row, row_lo, row_hi, d_ref, d_group_off, n_groups, k, snp_prior, d_out_rows,
+                   stream=None):
+    """_compute_posterior for the global rows [row_lo, row_hi) from consensus rows of 5 doubles starting at global row
+    `base_row`; writes rows of 5 = [P(A), P(C), P(G), P(T), coverage].  Enqueues only."""
+    lib = _cabi.require_device()
+    _cabi.check(lib.nvb_posterior_rows_d(int(device), ctypes.c_void_p(d_rows), int(base_row), int(row_lo), int(row_hi),
+                                         ctypes.c_void_p(d_ref), ctypes.c_void_p(d_group_off), int(n_groups), int(k),
+                                         float(snp_prior), ctypes.c_void_p(d_out_rows), _stream(stream)),
+                'nvb_posterior_rows_d')
 
 
 # ---- the two functions of the reference module, one read per call ------------------------------------------

@@ -158,7 +158,8 @@ class ProbabilityEstimator:
             return results
         signals = [it.read.normalized_signal[it.signal_range[0]:it.signal_range[1]] for it in items]
         with self._batch(items, signals) as batch:
-            batch.refine(self.model_transitions)
+            # every kernel of the batch runs on the caller's current torch stream; the getters below read back on it
+            batch.refine(self.model_transitions, _current_stream(self.kmer_model))
             tables = batch.alignment_tables([it.signal_range[0] for it in items],
                                             [it.apx.reference_range[0] for it in items],
                                             [it.apx.reference_range[1] for it in items],
@@ -189,8 +190,9 @@ class ProbabilityEstimator:
             return [], None
         signals = [it.read.normalized_signal[it.signal_range[0]:it.signal_range[1]] for it in items]
         batch = self._batch(items, signals)
+        stream = _current_stream(self.kmer_model)  # one stream for the whole path: refine, splines, estimate, posterior
         if self.tweak_signal_normalization:
-            batch.refine(False)
+            batch.refine(False, stream)
             events, _ = batch.events()
             expected = self.kmer_model.get_expected_signal_batch([it.reference_part for it in items],
                                                                  [it.context_before for it in items],
@@ -211,8 +213,8 @@ class ProbabilityEstimator:
             # resident signal slices (read.py:94), which therefore never travel back to the host
             splines = [it.read.fit_tweak_spline(ev.astype(int) + it.signal_range[0], exp_sig, means)
                        for it, ev, exp_sig, means in zip(items, events, expected, event_means)]
-            batch.apply_splines(splines)
-        batch.estimate(self.model_wobbling)
+            batch.apply_splines(splines, stream)
+        batch.estimate(self.model_wobbling, stream)
         return items, batch
 
     def _estimate_log_likelihoods(self, reference, read):
@@ -272,11 +274,13 @@ class ProbabilityEstimator:
                       coverage[group_off[i]:group_off[i + 1]].copy()) for i, g in enumerate(groups)]
 
     def posterior_stage(self, batch, reverse, intervals, reference, independent=False, process_group=None,
-                        plan=None):
+                        plan=None, collective='auto', events=None):
         """Device half of estimate_probabilities after the raw log-likelihoods exist in `batch`: normalise / flip,
-        scatter-add into the concatenated groups, all-reduce (consensus over several ranks), posterior stencil.
-        Returns (groups, group_off, probabilities tensor (total,4), coverage tensor (total,)) or None.  `plan` (from
-        ``plan_groups``) can be reused between calls with the same intervals."""
+        scatter-add into the concatenated groups, the exchange between ranks (consensus mode only, see
+        ``consensus_exchange``), posterior stencil.  Returns (groups, group_off, probabilities tensor (total,4),
+        coverage tensor (total,)) or None.  `plan` (from ``plan_groups``) can be reused between calls with the same
+        intervals; `events`, a dict, receives CUDA event pairs around the exchange (``events['exchange']``) and its
+        payload in bytes."""
         import torch
         dev = _device(self.kmer_model)
         stream = torch.cuda.current_stream()
@@ -288,19 +292,23 @@ class ProbabilityEstimator:
         groups, group_off, dest, d_ref = plan[:4]
         d_group_off = plan[4] if len(plan) > 4 else torch.as_tensor(group_off, device=dev)
         total = int(group_off[-1])
-        acc = torch.zeros((total, 4), dtype=torch.float64, device=dev)
-        cov = torch.zeros(total, dtype=torch.int32, device=dev)
+        k = self.kmer_model.get_k()
+        world = dist.get_world_size(process_group) if (dist is not None and not independent) else 1
+        slice_rows, total_pad = slice_geometry(total, world)
+        # consensus rows [sum A, sum C, sum G, sum T, coverage] (estimator.py:226-231): one buffer, one collective
+        rows = torch.zeros((total_pad, 5), dtype=torch.float64, device=dev)
         if batch is not None:
             d_chunks = torch.empty((batch.pack.total_reference, 4), dtype=torch.float64, device=dev)
             batch.chunk_values(reverse, self.normalization_event_length, d_chunks.data_ptr(), stream)
-            batch.scatter_add(d_chunks.data_ptr(), dest, acc.data_ptr(), cov.data_ptr(), stream)
-        if dist is not None and not independent:
-            dist.all_reduce(acc, group=process_group)  # the one exchange step (estimator.py:228-231)
-            dist.all_reduce(cov, group=process_group)
-        out = torch.empty_like(acc)
-        dtw.posterior_resident(dev.index, acc.data_ptr(), d_ref.data_ptr(), d_group_off.data_ptr(), len(groups), total,
-                               self.kmer_model.get_k(), self.snp_prior, out.data_ptr(), stream)
-        return groups, group_off, out, cov
+            batch.scatter_add_rows(d_chunks.data_ptr(), dest, rows.data_ptr(), stream)
+
+        def posterior_rows(local, base_row, row_lo, row_hi, out_rows):
+            dtw.posterior_rows(dev.index, local.data_ptr(), base_row, row_lo, row_hi, d_ref.data_ptr(),
+                               d_group_off.data_ptr(), len(groups), k, self.snp_prior, out_rows.data_ptr(), stream)
+
+        out = consensus_exchange(rows, total, k - 1, process_group if world > 1 else None, posterior_rows, collective,
+                                 events)
+        return groups, group_off, out[:total, :4].contiguous(), out[:total, 4].to(torch.int32)
 
     def plan_groups(self, intervals, reference, independent=False, process_group=None):
         """Host planning of the overlap groups (estimator.py:205-220): (groups, group_off, dest rows of the local
@@ -315,6 +323,84 @@ class ProbabilityEstimator:
         d_ref = torch.as_tensor(ref_codes, device=dev)
         d_group_off = torch.as_tensor(group_off, device=dev)
         return groups, group_off, dest, d_ref, d_group_off
+
+
+def slice_geometry(total, world):
+    """Rows per rank and padded row count when the concatenated groups are cut into `world` equal genome slices."""
+    rows = -(-max(total, 1) // world)
+    return rows, rows * world
+
+
+def consensus_exchange(rows, total, halo, process_group, posterior_rows, collective='auto', events=None):
+    """The one exchange step of consensus mode (estimator.py:226-231: per-position sums over the reads of ALL ranks)
+    followed by the posterior stencil.  `rows` is this rank's (total_pad, 5) accumulator [A, C, G, T, coverage].
+
+      'reduce_scatter' (default for several ranks): ONE reduce-scatter leaves every rank with the reduced rows of its
+          own genome slice; a tiny all-gather brings in the k-1 = `halo` reduced rows either side of it (the posterior
+          window, estimator.py:135-136); each rank computes the posterior of its slice only; ONE all-gather
+          distributes probabilities and coverage.  Traffic per rank: (N-1)/N of the buffer each way.
+      'allreduce': one all-reduce of the whole buffer, posterior replicated on every rank.
+      no process group: posterior over the local rows.
+
+    `posterior_rows(local, base_row, row_lo, row_hi, out_rows)` computes rows [row_lo, row_hi) from `local`, whose
+    first row is global row `base_row`, into `out_rows` (rows of 5 = probabilities + coverage).  Works on CUDA tensors
+    (NCCL) and on CPU tensors (gloo, the CPU tests).  Returns (>= total, 5) rows."""
+    import torch
+    if process_group is None:
+        out = torch.empty_like(rows)
+        posterior_rows(rows, 0, 0, total, out)
+        return out
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+    slice_rows, total_pad = slice_geometry(total, world)
+    assert rows.shape[0] == total_pad and rows.shape[1] == 5
+    mode = collective
+    if mode == 'auto':
+        mode = 'reduce_scatter' if (world > 1 and slice_rows >= halo) else 'allreduce'
+    timing = events is not None and rows.is_cuda
+    if timing:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    if mode == 'allreduce':
+        dist.all_reduce(rows, group=process_group)
+        if timing:
+            e1.record()
+            events['exchange'] = [(e0, e1)]
+            events['bus_bytes'] = rows.numel() * 8 * 2 * (world - 1) / world
+        out = torch.empty_like(rows)
+        posterior_rows(rows, 0, 0, total, out)
+        if events is not None:
+            events['mode'] = mode
+        return out
+    local = torch.zeros((slice_rows + 2 * halo, 5), dtype=rows.dtype, device=rows.device)
+    dist.reduce_scatter_tensor(local[halo:halo + slice_rows].view(-1), rows.view(-1), group=process_group)
+    if halo > 0:
+        edges = torch.cat([local[halo:2 * halo], local[slice_rows:slice_rows + halo]])  # own first / last halo rows
+        all_edges = torch.empty((world, 2 * halo, 5), dtype=rows.dtype, device=rows.device)
+        dist.all_gather_into_tensor(all_edges.view(-1), edges.reshape(-1), group=process_group)
+        if rank > 0:
+            local[:halo] = all_edges[rank - 1, halo:]
+        if rank < world - 1:
+            local[halo + slice_rows:] = all_edges[rank + 1, :halo]
+    if timing:
+        e1.record()
+    lo = rank * slice_rows
+    hi = max(lo, min(lo + slice_rows, total))
+    out_slice = torch.zeros((slice_rows, 5), dtype=rows.dtype, device=rows.device)
+    posterior_rows(local, lo - halo, lo, hi, out_slice)
+    if timing:
+        e2 = torch.cuda.Event(enable_timing=True)
+        e3 = torch.cuda.Event(enable_timing=True)
+        e2.record()
+    out = torch.empty((total_pad, 5), dtype=rows.dtype, device=rows.device)
+    dist.all_gather_into_tensor(out.view(-1), out_slice.view(-1), group=process_group)
+    if timing:
+        e3.record()
+        events['exchange'] = [(e0, e1), (e2, e3)]
+        events['bus_bytes'] = 2 * rows.numel() * 8 * (world - 1) / world
+    if events is not None:
+        events['mode'] = mode
+    return out
 
 
 def plan_groups_host(intervals, independent=False, process_group=None):
@@ -363,6 +449,13 @@ def shard_reads(work, world_size):
         shards[r].append(int(idx))
         load[r] += work[idx]
     return [sorted(s) for s in shards]
+
+
+def _current_stream(kmer_model):
+    """torch's current stream on the model's device (the kernels of a call are enqueued on it, so the estimator may
+    be used under ``with torch.cuda.stream(s)``)."""
+    import torch
+    return torch.cuda.current_stream(_device(kmer_model))
 
 
 def _device(kmer_model):

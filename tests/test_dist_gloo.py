@@ -154,3 +154,84 @@ def test_distributed_median_is_exact_gloo(tmp_path):
     for r in range(world):
         res = np.load(os.path.join(str(tmp_path), 'median%d.npy' % r))
         assert np.array_equal(res[:, 0], res[:, 1]), res
+
+
+def _numpy_posterior_rows(ref_codes, group_off, k, prior):
+    """posterior_rows callback for consensus_exchange on CPU tensors: _compute_posterior (estimator.py:123-156) for
+    the rows [row_lo, row_hi), reading ONLY the local rows it is given (slice + halo)."""
+    def fn(local, base_row, row_lo, row_hi, out_rows):
+        loc = local.numpy()
+        out = out_rows.numpy()
+        for g in range(row_lo, row_hi):
+            gi = int(np.searchsorted(group_off, g, side='right')) - 1
+            gs, ge = int(group_off[gi]), int(group_off[gi + 1])
+            i, L = g - gs, ge - gs
+            cs, ce = max(0, i - k + 1), min(i + k, L)
+            win = loc[gs + cs - base_row:gs + ce - base_row, :4]
+            mx = win.max()
+            c = 3
+            snp = 1 / ((1 - prior) / (prior / c) + (1 - (ce - cs - 1)) * c)
+            nonsnp = 1 - snp * c
+            pr = np.zeros(4)
+            for j in range(4):
+                pr[j] = np.exp(loc[g - base_row, j] - mx) * (nonsnp if j == ref_codes[g] else snp)
+                if j == ref_codes[g]:
+                    for i2 in range(cs, ce):
+                        if i2 == i:
+                            continue
+                        for j2 in range(4):
+                            if j2 != ref_codes[gs + i2]:
+                                pr[j] += np.exp(loc[gs + i2 - base_row, j2] - mx) * snp
+            out[g - row_lo, :4] = pr / sum(pr)
+            out[g - row_lo, 4] = loc[g - base_row, 4]
+    return fn
+
+
+def _exchange_worker(rank, world, port, result_dir, collective):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from nadavca_b200.estimator import consensus_exchange, plan_groups_host, shard_reads, slice_geometry
+        intervals, values = _make_chunks()
+        mine = shard_reads([e - s for s, e in intervals], world)[rank]
+        groups, group_off, dest = plan_groups_host([intervals[i] for i in mine], False, dist.group.WORLD)
+        total = int(group_off[-1])
+        slice_rows, total_pad = slice_geometry(total, world)
+        rows = torch.zeros((total_pad, 5), dtype=torch.float64)
+        for d, i in zip(dest, mine):
+            n = intervals[i][1] - intervals[i][0]
+            rows[d:d + n, :4] += torch.from_numpy(values[i])
+            rows[d:d + n, 4] += 1
+        ref_codes = np.random.default_rng(8).integers(0, 4, size=total)
+        k, prior = 6, 0.001
+        out = consensus_exchange(rows, total, k - 1, dist.group.WORLD, _numpy_posterior_rows(ref_codes, group_off, k, prior),
+                                 collective)
+        np.savez(os.path.join(result_dir, 'x%d.npz' % rank), out=out.numpy()[:total], group_off=group_off)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('collective', ['reduce_scatter', 'allreduce'])
+def test_consensus_exchange_slices_equal_single_process_gloo(tmp_path, collective):
+    """Reduce-scatter by genome slice + halo rows + posterior on the owned slice + all-gather == the posterior of the
+    summed chunks computed in one process (and == the all-reduce variant), on two gloo ranks."""
+    from nadavca_b200.estimator import consensus_exchange
+    world = 2
+    mp.spawn(_exchange_worker, args=(world, _free_port(), str(tmp_path), collective), nprocs=world, join=True)
+    intervals, values = _make_chunks()
+    want = _single_process(intervals, values)
+    total = sum(e - s for s, e, _, _ in want)
+    group_off = np.concatenate([[0], np.cumsum([e - s for s, e, _, _ in want])])
+    rows = torch.zeros((total, 5), dtype=torch.float64)
+    for gi, (s, e, acc, cov) in enumerate(want):
+        rows[group_off[gi]:group_off[gi + 1], :4] = torch.from_numpy(acc)
+        rows[group_off[gi]:group_off[gi + 1], 4] = torch.from_numpy(cov.astype(np.float64))
+    ref_codes = np.random.default_rng(8).integers(0, 4, size=total)
+    single = consensus_exchange(rows, total, 5, None, _numpy_posterior_rows(ref_codes, group_off, 6, 0.001)).numpy()
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), 'x%d.npz' % r))
+        assert np.array_equal(got['group_off'], group_off)
+        np.testing.assert_allclose(got['out'][:, :4], single[:, :4], rtol=1e-12, atol=1e-300)
+        assert np.array_equal(got['out'][:, 4], single[:, 4])
+        np.testing.assert_allclose(got['out'][:, :4].sum(axis=1), 1.0, rtol=1e-12)

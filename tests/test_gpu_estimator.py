@@ -382,3 +382,26 @@ def test_bench_line_contract():
     par = line['parity']
     assert par['reads'] == 2 and par['event_mismatches'] == 0 and par['ll_mismatches'] == 0
     assert par['events_compared'] > 0 and par['max_ll_rel'] < 1e-9
+
+
+def test_estimator_on_a_non_default_torch_stream(golden_estimator, default_model):
+    """The estimator enqueues every kernel on torch's CURRENT stream (PyTorch's side streams are not ordered against
+    the legacy default stream): results under ``with torch.cuda.stream(s)`` equal the golden ones."""
+    import torch
+    g = golden_estimator
+    genome, reads, aligner, est, cfg = _setup(g, default_model, 1)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        # keep the default stream busy so that an unordered read of the results would see stale data
+        junk = torch.empty(64 << 20, device='cuda')
+        for _ in range(4):
+            junk.normal_()
+        groups = est.estimate_probabilities(genome, reads, independent=False)
+        tables = est.get_refined_alignments(reads)
+    side.synchronize()
+    assert len(groups) == int(g['tweak1/n_groups'])
+    for gi, c in enumerate(groups):
+        np.testing.assert_allclose(c.values, g['tweak1/group%d/probabilities' % gi], rtol=PROB_RTOL, atol=PROB_ATOL)
+        assert np.array_equal(c.coverage, g['tweak1/group%d/coverage' % gi])
+    for i, res in enumerate(tables):
+        assert np.array_equal(res[1], g['tweak1/read%d/alignment_table' % i])

@@ -334,3 +334,82 @@ def test_both_sweep_schedules_match_oracle(lib_built, default_model, sweep_sched
             cases.append((mean, sigma) + c[2:])
         _compare_batch(rng, cases, k, cp, mel, bw, mean, sigma)
     test_default_model_read_matches_oracle(default_model)
+
+
+def test_very_wide_band_row_inside_a_batch(lib_built):
+    """A basecaller stall: an anchor gap of 12 000 samples gives band rows wider than the shared-memory hand-off
+    rows of the striped sweep (~8.5 k columns); the read goes through the global hand-off rows and the other reads
+    of the batch are unaffected (the reference handles any band width)."""
+    from nadavca_b200 import dtw
+    from oracle import oracle as orc
+    rng = np.random.default_rng(61)
+    k, cp, mel, bw = 3, 1, 2, 20
+    mean = rng.normal(0, 1.2, size=64)
+    sigma = rng.uniform(0.25, 0.5, size=64)
+    normal = [make_case(rng, k, cp, 40, bw, mel)[2:] for _ in range(2)]
+    # the stalled read: 30 bases, the 13th event lasts 12 000 samples, anchors only outside the stall
+    n = 30
+    ref = rng.integers(0, 4, size=n)
+    padded = np.zeros(n + k, dtype=int)
+    padded[cp:cp + n] = ref
+    ids = np.zeros(n, dtype=int)
+    for j in range(k):
+        ids = ids * 4 + padded[j:j + n]
+    lengths = np.maximum(mel, rng.poisson(7, size=n))
+    lengths[12] = 12_000
+    starts = np.concatenate([[0], np.cumsum(lengths)[:-1]]) + bw
+    sig = np.clip(np.concatenate([rng.normal(0, 1, bw), np.repeat(mean[ids], lengths) +
+                                  rng.normal(0, 0.35, lengths.sum()), rng.normal(0, 1, bw)]), -5, 5)
+    keep = np.array([j for j in range(n) if j not in (11, 12, 13)])
+    anchors = np.stack([starts[keep], keep], axis=1)
+    stalled = (sig, ref, [], [], anchors)
+    cases = [normal[0], stalled, normal[1]]
+    gm = dtw.KmerModel(k, cp, 4, mean, sigma)
+    om = orc.OracleModel(k, cp, 4, mean, sigma, 'port')
+    with dtw.Batch(gm, *[[c[i] for c in cases] for i in range(5)], bw, mel) as batch:
+        widest = max(int((be - bs + 1).max()) for bs, be in batch.bands())
+        assert widest > 10_000
+        for flag in (False, True):
+            batch.refine(flag)
+            events, status = batch.events()
+            assert status.tolist() == [0, 0, 0]
+            for ev, c in zip(events, cases):
+                assert_same_path(ev, (mean, sigma) + tuple(c), bw, mel, om, flag)
+        batch.estimate(True)
+        lls, _ = batch.log_likelihoods()
+        for ll, c in zip(lls, cases):
+            want = np.array(orc.estimate_log_likelihoods(*c, bw, mel, om, True))
+            np.testing.assert_allclose(ll, want, rtol=LL_RTOL, atol=LL_ATOL)
+
+
+def test_batches_of_one_model_overlap_on_two_streams(lib_built):
+    """Every stream has its own DP workspace: two batches of ONE model in flight on two streams give exactly the
+    results of running them one after the other."""
+    import torch
+    from nadavca_b200 import dtw
+    rng = np.random.default_rng(71)
+    k, cp, mel, bw = 4, 2, 2, 14
+    mean = rng.normal(0, 1.2, size=256)
+    sigma = rng.uniform(0.2, 0.6, size=256)
+    gm = dtw.KmerModel(k, cp, 4, mean, sigma)
+    sets = [[make_case(rng, k, cp, int(rng.integers(80, 200)), bw, mel)[2:] for _ in range(24)] for _ in range(2)]
+    lists = [[[c[i] for c in cases] for i in range(5)] for cases in sets]
+    want = []
+    for ls in lists:
+        with dtw.Batch(gm, *ls, bw, mel) as b:
+            b.refine(True)
+            ev = [e.copy() for e in b.events()[0]]
+            b.estimate(True)
+            want.append((ev, [x.copy() for x in b.log_likelihoods()[0]]))
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    with dtw.Batch(gm, *lists[0], bw, mel) as a, dtw.Batch(gm, *lists[1], bw, mel) as b:
+        for rep in range(3):
+            a.refine(True, s1)
+            b.refine(True, s2)
+            a.estimate(True, s1)
+            b.estimate(True, s2)
+        for batch, (ev, ll) in ((a, want[0]), (b, want[1])):
+            for x, y in zip(batch.events()[0], ev):
+                assert np.array_equal(x, y)
+            for x, y in zip(batch.log_likelihoods()[0], ll):
+                assert np.array_equal(x, y)
