@@ -42,15 +42,26 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--reads', type=int, default=1000, help='reads per GPU (weak scaling)')
-    ap.add_argument('--bases', type=int, default=2000)
+    ap.add_argument('--config', type=int, default=1, choices=[0, 1, 2, 3, 4],
+                    help='BASELINE.json configs index: 1 = the headline workload (default; its line also carries the '
+                         'consensus step of configs[2]), 2 = the same line, 0 / 3 / 4 = tools/bench_configs.py')
+    ap.add_argument('--reads', type=int, default=None, help='reads per GPU (weak scaling); default per config')
+    ap.add_argument('--bases', type=int, default=None, help='bases per read; default per config')
+    ap.add_argument('--sweep-bandwidths', default='50,100,150,250,400,650,1000', help='--config 4')
+    ap.add_argument('--sweep-batches', default='1,8,64,512,4096', help='--config 4: reads per GPU')
     ap.add_argument('--genome', type=int, default=4_600_000, help='synthetic genome length (E. coli-sized: configs[2])')
     ap.add_argument('--no-consensus', action='store_true', help='skip the consensus-mode (configs[2]) step')
-    ap.add_argument('--bandwidth', type=int, default=150)
+    ap.add_argument('--bandwidth', type=int, default=None, help='default 150 (400 for --config 3)')
     ap.add_argument('--cpu-sample', type=int, default=0, help='reads in the CPU sample (0 = one per host core)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-overlap', action='store_true', help='skip the two-stream pipeline measurement')
-    return ap.parse_args()
+    a = ap.parse_args()
+    per_config = {0: (100, 2000, 150), 1: (1000, 2000, 150), 2: (1000, 2000, 150), 3: (62, 100_000, 400),
+                  4: (None, 2000, 150)}[a.config]
+    a.reads = a.reads if a.reads is not None else per_config[0]
+    a.bases = a.bases if a.bases is not None else per_config[1]
+    a.bandwidth = a.bandwidth if a.bandwidth is not None else per_config[2]
+    return a
 
 
 # ---- workload ----------------------------------------------------------------------------------------------------
@@ -127,6 +138,13 @@ def band_stats(bands, k, cp, wobbling=True):
         # ... every SNP task streams its start prefix row and its closing suffix row and writes one double
         bytes_['snp'] += int(3 * ((w[first] + w[last + 1]) * 12 + 8).sum())
     return cells, bytes_
+
+
+def band_cells_transitions(band):
+    """NextRow cells of refine_alignment(transitions) for one read's (starts, ends) band."""
+    bs, be = band
+    w = (be - bs + 1).astype(np.int64)
+    return int(2 * (2 * w.sum() - w[0] - w[-1]) - w[0] - w[-1])
 
 
 class ClockSampler:
@@ -675,5 +693,9 @@ if __name__ == '__main__':
         relaunch_under_torchrun(a)
     if a.impl == 'reference':
         run_reference(a)
+    elif a.config in (0, 3, 4):
+        sys.path.insert(0, os.path.join(ROOT, 'tools'))
+        import bench_configs
+        bench_configs.run(sys.modules[__name__], a)
     else:
         run_ours(a)
