@@ -33,8 +33,8 @@
 // Mantissas are renormalised when (step & mask) == mask, i.e. every 8 steps.  The period bounds how stale a
 // mantissa can get: alignment takes the larger EXPONENT, so a value whose mantissa has decayed hands its slack to
 // whatever is added to it, and the slack compounds lane after lane (one hop per step).  With at most 2^-1 per step
-// and hop (emission mantissas >= 0.70, transition weight 0.64 * 2^-6) 8 steps x 8 hops stay far inside the double
-// range; 32 steps did not (measured: garbage in the far tails of transition rows).
+// and hop (emission mantissas in [0.98, 1.98], transition weight 0.64 * 2^-6) 8 steps x 8 hops stay far inside the
+// double range; 32 steps did not (measured: garbage in the far tails of transition rows).
 #ifndef NVB_RENORM_MASK
 #define NVB_RENORM_MASK 7
 #endif
@@ -45,33 +45,58 @@
 #define NVB_LN2_LO 1.90821492927058770002e-10
 #define NVB_LOG2E 1.44269504088896338700e+00
 
-// Taylor coefficients 1/13! .. 1/3! of exp(r); read as constant-bank operands of the DFMAs
-static __constant__ double c_exp_poly[11] = {
-    1.6059043836821613e-10, 2.08767569878681e-09,   2.505210838544172e-08,  2.755731922398589e-07,
-    2.7557319223985893e-06, 2.48015873015873e-05,   1.984126984126984e-04,  1.388888888888889e-03,
-    8.333333333333333e-03,  4.1666666666666664e-02, 1.6666666666666666e-01};
-
 // 2^e as a double for e <= 0; e <= -1023 gives +0.0
 __device__ __forceinline__ double pow2neg(int e) {
   e = max(e, -1023);
   return __hiloint2double((e + 1023) << 20, 0);
 }
 
-// exp(l) = p * 2^k with p in [0.70, 1.42], any finite l (no underflow: k is returned, not applied).
-// Cody-Waite reduction r = l - k*ln2 (hi/lo) and a degree-13 Taylor polynomial on |r| <= 0.347 (error < 5e-18).
+// exp(l) = p * 2^k with p in [0.98, 1.98], any finite l (no underflow: k is returned, not applied).
+// l = (32 k + j) ln2/32 + r, |r| <= ln2/64: Cody-Waite reduction against ln2/32 (hi/lo; the hi part has 32 significant
+// bits, so n * hi is exact for |n| < 2^21), 2^(j/32) from a 32-entry table in shared memory, exp(r) - 1 by a degree-6
+// Taylor polynomial (truncation 3.5e-18; worst relative error of p measured against 60-digit arithmetic: 2.0e-16).
+// The table replaces 6 of the 13 dependent DFMAs of the single-interval polynomial this started as: the FP64 pipe
+// issues one warp instruction every two cycles, and in the latency-bound sweeps the Horner chain is on the critical path.
+#define NVB_32_LOG2E 46.16624130844683
+#define NVB_LN2_32_HI 0.02166084938653512
+#define NVB_LN2_32_LO 5.9631716539705866e-12
+
+static __constant__ double c_exp_tab[32] = {
+    1.0,                1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577,
+    1.1143867425958924, 1.1387886347566916, 1.1637248587775775, 1.189207115002721,  1.215247359980469,
+    1.241857812073484,  1.2690509571917332, 1.2968395546510096, 1.3252366431597413, 1.3542555469368927,
+    1.383909881963832,  1.4142135623730951, 1.4451808069770467, 1.4768261459394993, 1.5091644275934228,
+    1.5422108254079407, 1.5759808451078865, 1.6104903319492543, 1.645755478153965,  1.681792830507429,
+    1.718619298122478,  1.7562521603732995, 1.7947090750031072, 1.8340080864093424, 1.8741676341103,
+    1.9152065613971474, 1.9571441241754002};
+// 1/6! .. 1/3!; read as constant-bank operands of the DFMAs
+static __constant__ double c_exp_poly[4] = {1.388888888888889e-03, 8.333333333333333e-03, 4.1666666666666664e-02,
+                                            1.6666666666666666e-01};
+
+static __shared__ double s_exp_tab[32];
+
+// Every kernel that evaluates emissions calls this once, with ALL threads of the CTA, before anything else.
+__device__ __forceinline__ void exp_table_init() {
+  if (threadIdx.x < 32) s_exp_tab[threadIdx.x] = c_exp_tab[threadIdx.x];
+  __syncthreads();
+}
+
 __device__ __forceinline__ void exp_ext(double l, double &p, int &k) {
   const double magic = 6755399441055744.0;  // 1.5 * 2^52: rint via add/sub, integer in the low word
-  double t = fma(l, NVB_LOG2E, magic);
-  k = __double2loint(t);
-  double kd = t - magic;
-  double r = fma(-kd, NVB_LN2_HI, l);
-  r = fma(-kd, NVB_LN2_LO, r);
-  double q = c_exp_poly[0];
-#pragma unroll
-  for (int i = 1; i < 11; i++) q = fma(q, r, c_exp_poly[i]);
+  const double t = fma(l, NVB_32_LOG2E, magic);
+  const int n = __double2loint(t);
+  const double kd = t - magic;
+  double r = fma(-kd, NVB_LN2_32_HI, l);
+  r = fma(-kd, NVB_LN2_32_LO, r);
+  k = n >> 5;
+  const double T = s_exp_tab[n & 31];
+  double q = fma(c_exp_poly[0], r, c_exp_poly[1]);
+  q = fma(q, r, c_exp_poly[2]);
+  q = fma(q, r, c_exp_poly[3]);
   q = fma(q, r, 0.5);
   q = fma(q, r, 1.0);
-  p = fma(q, r, 1.0);
+  q *= r;             // exp(r) - 1
+  p = fma(T, q, T);
 }
 
 // natural log of f * 2^E (f > 0), E*ln2 added in two pieces

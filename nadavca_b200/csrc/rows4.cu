@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(224, 4) sweep4_kernel(ModelDev M, BatchDev B, 
   extern __shared__ unsigned long long smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x;  // (read, direction)
+  exp_table_init();
   if (item >= n_items) return;
   const int b = b0 + (item >> 1);
   if (B.flags[b]) return;

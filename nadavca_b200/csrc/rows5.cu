@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(64, NVB_ROT_MIN_BLOCKS) sweep5_kernel(ModelDev
   extern __shared__ unsigned long long smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * (blockDim.x >> 5) + warp;  // (read, direction)
+  exp_table_init();
   if (item >= n_items) return;
   const int b = b0 + (item >> 1);
   if (B.flags[b] != 0) return;  // bad band

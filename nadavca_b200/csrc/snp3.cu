@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(128) snp3_kernel(ModelDev M, BatchDev B, int b
                                                    const int32_t *pX, const double *sF, const int32_t *sX,
                                                    double *out_ll) {
   constexpr bool wobbling = (MODE == NVB_MODE_WOBBLE);
+  exp_table_init();
   const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t warp_id = blockIdx.x * (int64_t)(blockDim.x >> 5) + wic;
   const int A = M.alphabet;

@@ -405,3 +405,24 @@ def test_estimator_on_a_non_default_torch_stream(golden_estimator, default_model
         assert np.array_equal(c.coverage, g['tweak1/group%d/coverage' % gi])
     for i, res in enumerate(tables):
         assert np.array_equal(res[1], g['tweak1/read%d/alignment_table' % i])
+
+
+def test_meth_scores_on_gpu_alignments_match_reference_golden(golden_estimator, default_model):
+    """detect_meth's scoring (detect_meth.py:26-60) fed by the GPU path -- refined alignments and expected levels
+    from the device -- equals the golden scores the REFERENCE's detect_meth computed on its own alignments of the same
+    reads, bit for bit."""
+    from nadavca_b200.detect_meth import calculate_meth_scores, maxs3
+    g = golden_estimator
+    genome, reads, aligner, est, cfg = _setup(g, default_model, 1)
+    results = est.get_refined_alignments(reads)
+    total = 0
+    for i, (read, res) in enumerate(zip(reads, results)):
+        apx, table = res
+        cut = read.normalized_signal[table[0][1]:table[-1][2]]
+        feats = calculate_meth_scores(cut, table, apx, 'CG', default_model)
+        assert [f[0] for f in feats] == g['meth/read%d/positions' % i].tolist()
+        assert [f[1] for f in feats] == g['meth/read%d/contexts' % i].tolist()
+        assert np.array_equal(np.array([f[2] for f in feats]).reshape(-1, 11), g['meth/read%d/scores' % i])
+        assert [maxs3(f[2]) for f in feats] == g['meth/read%d/aggregated' % i].tolist()
+        total += len(feats)
+    assert total >= 10

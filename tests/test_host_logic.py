@@ -264,3 +264,35 @@ def test_bench_reference_arm_contract():
     assert line['e2e'] == {'value': line['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0,
                            'd2h_bytes_per_step': 0}
     assert 'workload' in line['config'] and line['vs_baseline'] is None
+
+
+def test_output_writers_keep_the_reference_layout(tmp_path):
+    """.npz of `nadavca align` (align_signal.py:83-132) and the SNP table of `nadavca snp` (estimator.py:21-31)."""
+    from nadavca_b200 import output
+    from nadavca_b200.alignment import ApproximateSignalAlignment
+    from nadavca_b200.estimator import Chunk
+    from nadavca_b200.read import Read
+    read = Read.from_arrays(np.arange(100, 160), 'ACGTAC', {i: 10 * i for i in range(6)})
+    apx = ApproximateSignalAlignment(np.zeros((0, 2), dtype=int), (0, 60), (7, 11), (1, 5), True,
+                                     np.array(list('GATT')), 'chr1')
+    table = np.array([[10, 5, 12], [9, 12, 20], [8, 20, 31], [7, 31, 40]])
+    path = output.write_alignment_npz(str(tmp_path / 'r0'), read, apx, table)
+    z = np.load(path)
+    assert z['arr_0'].tolist() == list(range(105, 131))          # raw signal from the first to the last event START
+    labels = z['arr_1']
+    assert len(labels) == 26 and labels[0] == 'G' and labels[7] == 'A' and labels[15] == 'T'
+    assert (labels != 'N').sum() == 3                            # the last base gets no label (alignment[:-1])
+    assert z['arr_2'].tolist() == ['7', '-', 'chr1', 'ACGTAC']
+    bad = table.copy()
+    bad[2, 1] = 12
+    with pytest.raises(output.AlignException):
+        output.sample_labels(apx, bad)
+    assert output.write_alignment_npz(str(tmp_path / 'e'), read, apx, np.array([[1, 5, 5], [2, 5, 9]])) is None
+    chunk = Chunk(2, 4, np.array([[0.25, 0.25, 0.25, 0.25], [1.0, 0.0, 0.0, 0.0]]), np.array([3, 1]))
+    output.write_snp_tables([chunk], 'ACGTACGT', str(tmp_path / 'snps.txt'))
+    lines = open(tmp_path / 'snps.txt').read().splitlines()
+    assert lines[0] == 'index\tbase\tcoverage\tA\tC\tG\tT'
+    assert lines[1] == '2\tG\t3\t' + '\t'.join(['0.2500000000000000'] * 4)
+    assert lines[2].startswith('3\tT\t1\t1.0000000000000000\t0.0000000000000000')
+    output.write_snp_tables([chunk, None], 'ACGTACGT', str(tmp_path / 'ind'), independent=True, names=['a.fast5', 'b'])
+    assert sorted(os.listdir(tmp_path / 'ind')) == ['a.txt']
