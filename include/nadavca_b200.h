@@ -174,6 +174,17 @@ int nvb_batch_chunk_values(nvb_batch *batch, const int32_t *reverse, double norm
  * for every read r with dest[r] >= 0 and status OK.  dest is a HOST array of n_reads row offsets. */
 int nvb_batch_scatter_add(nvb_batch *batch, const double *d_chunks, const int64_t *dest, double *d_acc,
                           int32_t *d_cov, void *stream);
+/* ---- pooled median / MAD normalisation on the device: replaces Read.normalize_reads (read.py:67-81) ------------
+ * One pass of an exact most-significant-digit radix select over the order-preserving 64-bit keys of d_values (or of
+ * |d_values - shift| when absolute_deviation != 0): ADDS to d_hist[256] the histogram of the 8 key bits below the
+ * `fixed_bits` (0, 8, .. 56) leading bits, over the values whose leading bits equal `prefix`.  Eight passes find an
+ * order statistic; a job sharded over GPUs all-reduces d_hist between the kernel and the bin choice.  Enqueues only. */
+int nvb_radix_histogram_d(int device, const double *d_values, int64_t n, int absolute_deviation, double shift,
+                          uint64_t prefix, int fixed_bits, uint64_t *d_hist, void *stream);
+/* d_out = clip((d_values - shift) / scale, lo, hi)  (read.py:80-81).  Enqueues only. */
+int nvb_normalize_clip_d(int device, const double *d_values, int64_t n, double shift, double scale, double lo, double hi,
+                         double *d_out, void *stream);
+
 /* Consensus accumulator as ROWS of 5 doubles [sum A, sum C, sum G, sum T, coverage] (estimator.py:226-231): sums and
  * coverage travel in one buffer, so the exchange between GPUs is one collective (reduce-scatter by genome slice, or
  * all-reduce).  d_rows is a zero-initialised device buffer of (total rows, 5) doubles; dest as in

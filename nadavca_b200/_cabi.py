@@ -81,6 +81,12 @@ SIGNATURES = {
                                               ctypes.c_void_p]),
     'nvb_batch_scatter_add': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_i64p, ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_void_p]),
+    'nvb_radix_histogram_d': (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                                             ctypes.c_double, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p,
+                                             ctypes.c_void_p]),
+    'nvb_normalize_clip_d': (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_double,
+                                            ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_void_p,
+                                            ctypes.c_void_p]),
     'nvb_batch_scatter_add_rows': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_i64p, ctypes.c_void_p,
                                                   ctypes.c_void_p]),
     'nvb_posterior_rows_d': (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,

@@ -949,6 +949,28 @@ int nvb_batch_scatter_add(nvb_batch *b, const double *d_chunks, const int64_t *d
   return NVB_OK;
 }
 
+int nvb_radix_histogram_d(int device, const double *d_values, int64_t n, int absolute_deviation, double shift,
+                          uint64_t prefix, int fixed_bits, uint64_t *d_hist, void *stream) {
+  if (!d_hist || n < 0 || (n > 0 && !d_values) || fixed_bits < 0 || fixed_bits > 56 || (fixed_bits & 7))
+    return fail(NVB_EINVAL, "bad argument");
+  if (nvb_device_count() <= device) return fail(NVB_ECUDA, "CUDA device %d not available (no CPU fallback)", device);
+  CU(cudaSetDevice(device));
+  nvbk_radix_hist(d_values, n, absolute_deviation ? 1 : 0, shift, (unsigned long long)prefix, fixed_bits,
+                  (unsigned long long *)d_hist, (cudaStream_t)stream);
+  CU(cudaGetLastError());
+  return NVB_OK;
+}
+
+int nvb_normalize_clip_d(int device, const double *d_values, int64_t n, double shift, double scale, double lo, double hi,
+                         double *d_out, void *stream) {
+  if (n < 0 || (n > 0 && (!d_values || !d_out))) return fail(NVB_EINVAL, "bad argument");
+  if (nvb_device_count() <= device) return fail(NVB_ECUDA, "CUDA device %d not available (no CPU fallback)", device);
+  CU(cudaSetDevice(device));
+  nvbk_normalize_clip(d_values, n, shift, scale, lo, hi, d_out, (cudaStream_t)stream);
+  CU(cudaGetLastError());
+  return NVB_OK;
+}
+
 int nvb_batch_scatter_add_rows(nvb_batch *b, const double *d_chunks, const int64_t *dest, double *d_rows, void *stream) {
   if (!b || !d_chunks || !dest || !d_rows) return fail(NVB_EINVAL, "NULL argument");
   CU(cudaSetDevice(b->model->device));

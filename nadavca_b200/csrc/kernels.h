@@ -58,5 +58,11 @@ void nvbk_posterior_rows(const double *d_rows, int64_t base, int64_t row_lo, int
                          cudaStream_t st);
 void nvbk_fill_status(const BatchDev &B, int32_t *d_status, double *d_ll, int alphabet, cudaStream_t st);
 
+// select.cu: pooled median / MAD normalisation (read.py:67-81)
+void nvbk_radix_hist(const double *d_values, int64_t n, int mode, double shift, unsigned long long prefix, int fixed,
+                     unsigned long long *d_hist, cudaStream_t st);
+void nvbk_normalize_clip(const double *d_values, int64_t n, double shift, double scale, double lo, double hi,
+                         double *d_out, cudaStream_t st);
+
 // microbench.cu
 float nvbk_fp64_fma_probe(int iters, int blocks, cudaStream_t st, double *d_sink);

@@ -49,6 +49,7 @@ def estimate_snps(reference_filename,
         if isinstance(read, str):
             reads[i] = Read.load_from_fast5(read, group_name)
     # ONE median/MAD pooled over all reads (estimate_snps.py:61) -- over the reads of all ranks in a sharded job
-    Read.normalize_reads(reads, process_group)
+    # ... on the device: exact radix select of the two medians + clip kernel (csrc/select.cu)
+    Read.normalize_reads(reads, process_group, device=kmer_model.device)
     return estimator.estimate_probabilities(reference, reads, independent=independent,
                                             process_group=process_group)

@@ -95,6 +95,7 @@ class ProbabilityEstimator:
         self.normalization_event_length = config['normalization_event_length']
         self.tweak_signal_normalization = config['tweak_signal_normalization']
         self.workspace_limit = config.get('workspace_limit_bytes', 0) if hasattr(config, 'get') else 0
+        self.sub_batch_reads = config.get('sub_batch_reads', 256) if hasattr(config, 'get') else 256
         self.last_stats = {}
 
     # ---- small host helpers with the reference's names ------------------------------------------------------
@@ -182,40 +183,77 @@ class ProbabilityEstimator:
 
     # ---- path B: log-likelihood chunks ---------------------------------------------------------------------------
     def _run_estimate(self, reference, reads):
-        """Shared front half of path B.  Returns (items, batch) with raw log-likelihoods resident on the device, or
-        ([], None).  Reads whose approximate alignment or refinement fails are dropped (the reference returns None /
-        crashes in splrep for them)."""
+        """Shared front half of path B.  Returns (items, subs): the prepared reads that aligned and have a path, and
+        a list of (batch, count) sub-batches covering them in order, raw log-likelihoods resident on the device -- or
+        ([], []).  Reads whose approximate alignment or refinement fails are dropped (the reference returns None /
+        crashes in splrep for them).
+
+        The reads are cut into sub-batches of ``sub_batch_reads`` (config key, default 256), each on its own CUDA
+        stream (per-stream DP workspaces, csrc/api.cu), so that the host work between the two DP calls -- D2H of the
+        event means, the FITPACK spline fits (worker processes), H2D of the splines -- of one sub-batch overlaps the
+        kernels of the others."""
+        import torch
+        from .read import fit_splines_async
         items = [it for it in (self._prepare(read, reference) for read in reads) if it is not None]
         if not items:
-            return [], None
-        signals = [it.read.normalized_signal[it.signal_range[0]:it.signal_range[1]] for it in items]
-        batch = self._batch(items, signals)
-        stream = _current_stream(self.kmer_model)  # one stream for the whole path: refine, splines, estimate, posterior
+            return [], []
+        main = _current_stream(self.kmer_model)
+        per = max(1, int(self.sub_batch_reads))
+        n_sub = -(-len(items) // per)
+        bounds = [len(items) * j // n_sub for j in range(n_sub + 1)]
+        streams = [torch.cuda.Stream(device=_device(self.kmer_model)) for _ in range(min(n_sub, 4))] if n_sub > 1 \
+            else [main]
+        subs = []
+        for j in range(n_sub):
+            sub_items = items[bounds[j]:bounds[j + 1]]
+            st = streams[j % len(streams)]
+            st.wait_stream(main)
+            batch = self._batch(sub_items, [it.read.normalized_signal[it.signal_range[0]:it.signal_range[1]]
+                                            for it in sub_items])
+            if self.tweak_signal_normalization:
+                batch.refine(False, st)
+            subs.append([batch, sub_items, st])
         if self.tweak_signal_normalization:
-            batch.refine(False, stream)
-            events, _ = batch.events()
-            expected = self.kmer_model.get_expected_signal_batch([it.reference_part for it in items],
-                                                                 [it.context_before for it in items],
-                                                                 [it.context_after for it in items])
-            keep = [i for i, ev in enumerate(events) if ev is not None]
-            event_means = batch.event_means()  # per-event signal means, computed next to the resident events
-            if len(keep) != len(items):
-                event_means = [event_means[i] for i in keep]
-                batch.close()
-                items = [items[i] for i in keep]
-                events = [events[i] for i in keep]
-                expected = [expected[i] for i in keep]
-                if not items:
-                    return [], None
-                signals = [signals[i] for i in keep]
-                batch = self._batch(items, signals)
-            # host: the smoothing-spline FIT per read (scipy splrep, read.py:93); device: its EVALUATION over the
-            # resident signal slices (read.py:94), which therefore never travel back to the host
-            splines = [it.read.fit_tweak_spline(ev.astype(int) + it.signal_range[0], exp_sig, means)
-                       for it, ev, exp_sig, means in zip(items, events, expected, event_means)]
-            batch.apply_splines(splines, stream)
-        batch.estimate(self.model_wobbling, stream)
-        return items, batch
+            fits = []
+            for sub in subs:
+                batch, sub_items, st = sub
+                events, _ = batch.events()
+                event_means = batch.event_means()  # per-event signal means, computed next to the resident events
+                keep = [i for i, ev in enumerate(events) if ev is not None]
+                if len(keep) != len(sub_items):
+                    batch.close()
+                    sub_items = [sub_items[i] for i in keep]
+                    event_means = [event_means[i] for i in keep]
+                    if sub_items:
+                        batch = self._batch(sub_items, [it.read.normalized_signal[it.signal_range[0]:it.signal_range[1]]
+                                                        for it in sub_items])
+                    else:
+                        batch = None
+                    sub[0], sub[1] = batch, sub_items
+                expected = self.kmer_model.get_expected_signal_batch([it.reference_part for it in sub_items],
+                                                                     [it.context_before for it in sub_items],
+                                                                     [it.context_after for it in sub_items]) \
+                    if sub_items else []
+                # host: the smoothing-spline FIT per read (scipy splrep, read.py:93), in worker processes
+                fits.append(fit_splines_async(zip(event_means, expected)))
+            for (batch, sub_items, st), fit in zip(subs, fits):
+                if batch is None:
+                    continue
+                splines = fit.get()
+                for it, spline in zip(sub_items, splines):
+                    it.read.tweak_spline = spline
+                    it.read.tweaked_normalized_signal = None
+                # device: the spline EVALUATION over the resident signal slices (read.py:94), which therefore never
+                # travel back to the host
+                batch.apply_splines(splines, st)
+                batch.estimate(self.model_wobbling, st)
+        else:
+            for batch, sub_items, st in subs:
+                batch.estimate(self.model_wobbling, st)
+        for _, _, st in subs:
+            main.wait_stream(st)
+        subs = [(batch, sub_items) for batch, sub_items, _ in subs if batch is not None]
+        return [it for _, sub_items in subs for it in sub_items], [(batch, len(sub_items)) for batch, sub_items in subs]
 
     def _estimate_log_likelihoods(self, reference, read):
         """estimator.py:59-121 for one read: Chunk of normalised, strand-corrected log-likelihoods or None."""
@@ -224,20 +262,28 @@ class ProbabilityEstimator:
 
     def estimate_log_likelihood_chunks(self, reference, reads):
         import torch
-        items, batch = self._run_estimate(reference, reads)
-        if batch is None:
+        items, subs = self._run_estimate(reference, reads)
+        if not subs:
             return []
+        stream = _current_stream(self.kmer_model)
+        out = []
         try:
-            total = batch.pack.total_reference
-            d_chunks = torch.empty((total, 4), dtype=torch.float64, device=_device(self.kmer_model))
-            batch.chunk_values([int(it.apx.reverse_complement) for it in items], self.normalization_event_length,
-                               d_chunks.data_ptr(), torch.cuda.current_stream())
-            values = d_chunks.cpu().numpy()
-            off = batch.pack.reference_off
+            lo = 0
+            for batch, count in subs:
+                sub_items = items[lo:lo + count]
+                lo += count
+                d_chunks = torch.empty((batch.pack.total_reference, 4), dtype=torch.float64,
+                                       device=_device(self.kmer_model))
+                batch.chunk_values([int(it.apx.reverse_complement) for it in sub_items],
+                                   self.normalization_event_length, d_chunks.data_ptr(), stream)
+                values = d_chunks.cpu().numpy()
+                off = batch.pack.reference_off
+                out.extend(Chunk(it.apx.reference_range[0], it.apx.reference_range[1], values[off[i]:off[i + 1]].copy())
+                           for i, it in enumerate(sub_items))
         finally:
-            batch.close()
-        return [Chunk(it.apx.reference_range[0], it.apx.reference_range[1], values[off[i]:off[i + 1]].copy())
-                for i, it in enumerate(items)]
+            for batch, _ in subs:
+                batch.close()
+        return out
 
     def _compute_posterior(self, log_likelihoods, reference):
         """estimator.py:131-156 for one group, on the device."""
@@ -255,9 +301,9 @@ class ProbabilityEstimator:
         with one call per read, estimate_snps.py:63-68) and returns one Chunk per aligned read in input order.
         Otherwise chunks are summed per overlap group; with an initialised torch.distributed `process_group` the
         reads given to each rank are that rank's shard and the per-position sums are all-reduced over NCCL."""
-        items, batch = self._run_estimate(reference, reads)
+        items, subs = self._run_estimate(reference, reads)
         try:
-            stage = self.posterior_stage(batch, [int(it.apx.reverse_complement) for it in items],
+            stage = self.posterior_stage(subs, [int(it.apx.reverse_complement) for it in items],
                                          [tuple(it.apx.reference_range) for it in items], reference, independent,
                                          process_group)
             if stage is None:
@@ -265,17 +311,19 @@ class ProbabilityEstimator:
             groups, group_off, out, cov = stage
             probabilities = out.cpu().numpy()
             coverage = cov.cpu().numpy().astype(int)
-            self.last_stats = {'launches': (batch.launch_count if batch is not None else 0) + 1,
-                               'groups': len(groups), 'positions': int(group_off[-1])}
+            self.last_stats = {'launches': sum(batch.launch_count for batch, _ in subs) + 1,
+                               'groups': len(groups), 'positions': int(group_off[-1]), 'sub_batches': len(subs)}
         finally:
-            if batch is not None:
+            for batch, _ in subs:
                 batch.close()
         return [Chunk(g[0], g[1], probabilities[group_off[i]:group_off[i + 1]].copy(),
                       coverage[group_off[i]:group_off[i + 1]].copy()) for i, g in enumerate(groups)]
 
     def posterior_stage(self, batch, reverse, intervals, reference, independent=False, process_group=None,
                         plan=None, collective='auto', events=None):
-        """Device half of estimate_probabilities after the raw log-likelihoods exist in `batch`: normalise / flip,
+        """Device half of estimate_probabilities after the raw log-likelihoods exist in `batch` (one ``dtw.Batch``,
+        None, or the list of (batch, read count) sub-batches of ``_run_estimate``; `reverse` / `intervals` cover the
+        reads of all sub-batches in order): normalise / flip,
         scatter-add into the concatenated groups, the exchange between ranks (consensus mode only, see
         ``consensus_exchange``), posterior stencil.  Returns (groups, group_off, probabilities tensor (total,4),
         coverage tensor (total,)) or None.  `plan` (from ``plan_groups``) can be reused between calls with the same
@@ -297,10 +345,13 @@ class ProbabilityEstimator:
         slice_rows, total_pad = slice_geometry(total, world)
         # consensus rows [sum A, sum C, sum G, sum T, coverage] (estimator.py:226-231): one buffer, one collective
         rows = torch.zeros((total_pad, 5), dtype=torch.float64, device=dev)
-        if batch is not None:
-            d_chunks = torch.empty((batch.pack.total_reference, 4), dtype=torch.float64, device=dev)
-            batch.chunk_values(reverse, self.normalization_event_length, d_chunks.data_ptr(), stream)
-            batch.scatter_add_rows(d_chunks.data_ptr(), dest, rows.data_ptr(), stream)
+        subs = batch if isinstance(batch, (list, tuple)) else ([(batch, len(reverse))] if batch is not None else [])
+        lo = 0
+        for sub, count in subs:
+            d_chunks = torch.empty((sub.pack.total_reference, 4), dtype=torch.float64, device=dev)
+            sub.chunk_values(reverse[lo:lo + count], self.normalization_event_length, d_chunks.data_ptr(), stream)
+            sub.scatter_add_rows(d_chunks.data_ptr(), dest[lo:lo + count], rows.data_ptr(), stream)
+            lo += count
 
         def posterior_rows(local, base_row, row_lo, row_hi, out_rows):
             dtw.posterior_rows(dev.index, local.data_ptr(), base_row, row_lo, row_hi, d_ref.data_ptr(),

@@ -51,14 +51,25 @@ class Read:
             'build reads with Read.from_arrays(raw_signal, sequence, sequence_to_signal_mapping)')
 
     @staticmethod
-    def normalize_reads(reads, process_group=None):
+    def normalize_reads(reads, process_group=None, device=None):
         """One median / MAD pooled over all given reads, clipped to +-5 (read.py:67-81).
 
         With a torch.distributed `process_group` the reads of ALL ranks are pooled (every rank passes its shard): the
         two medians are exact order statistics found by bisection on the float64 bit pattern with one small
-        all-reduce of counts per step, so a sharded job normalises exactly like the reference does on one host."""
+        all-reduce of counts per step, so a sharded job normalises exactly like the reference does on one host.
+
+        With `device` (a CUDA ordinal) the pooled samples are normalised ON THE GPU: exact radix select of the two
+        medians (8 histogram passes each, the 256-bin histograms all-reduced over `process_group` when given) and the
+        clip kernel; the result is bit-identical to the host path."""
         values = numpy.concatenate([numpy.asarray(read.raw_signal, dtype=float) for read in reads]) \
             if len(reads) else numpy.zeros(0)
+        if device is not None:
+            normalized = _normalize_on_device(values, int(device), process_group)
+            start = 0
+            for read in reads:
+                read.normalized_signal = normalized[start:start + len(read.raw_signal)]
+                start += len(read.raw_signal)
+            return
         if process_group is None:
             shift = float(numpy.median(values))
             scale = float(numpy.median(abs(values - shift)))
@@ -83,16 +94,114 @@ class Read:
         sorted by (mean, expected) like the reference's list of tuples."""
         if event_means is None:
             event_means = [numpy.mean(self.normalized_signal[event[0]: event[1]]) for event in alignment]
-        means = numpy.asarray(event_means, dtype=float)
-        expected = numpy.asarray(expected_means, dtype=float)
-        with numpy.errstate(invalid='ignore'):
-            keep = numpy.abs(expected - means) <= 1  # a NaN mean (empty event) fails the test, as in the reference
-        means, expected = means[keep], expected[keep]
-        order = numpy.lexsort((expected, means))
-        means, expected = means[order], expected[order]
-        self.tweak_spline = interpolate.splrep(means, expected, s=len(means))
+        self.tweak_spline = fit_spline(event_means, expected_means)
         self._tweaked_normalized_signal = None
         return self.tweak_spline
+
+
+def fit_spline(event_means, expected_means):
+    """read.py:87-93 for one read: (observed event mean, expected level) pairs -> scipy.interpolate.splrep."""
+    means = numpy.asarray(event_means, dtype=float)
+    expected = numpy.asarray(expected_means, dtype=float)
+    with numpy.errstate(invalid='ignore'):
+        keep = numpy.abs(expected - means) <= 1  # a NaN mean (empty event) fails the test, as in the reference
+    means, expected = means[keep], expected[keep]
+    order = numpy.lexsort((expected, means))
+    means, expected = means[order], expected[order]
+    return interpolate.splrep(means, expected, s=len(means))
+
+
+def _fit_spline_job(job):
+    return fit_spline(*job)
+
+
+_FIT_POOL = None
+
+
+class _Ready:
+    """Result holder with the ``get()`` of multiprocessing's AsyncResult."""
+
+    def __init__(self, value):
+        self.value = value
+
+    def get(self):
+        return self.value
+
+
+def fit_splines_async(jobs, workers=None):
+    """``fit_spline`` for many reads; returns a handle whose ``get()`` gives the list of splines.  The FITPACK fit is host work that the reference does one read at a time
+    (0.3-1 ms each, holding the GIL); batches of 32 reads or more go through a persistent pool of worker processes
+    (``forkserver``: the workers never see this process's CUDA context), which runs the SAME scipy call, so the
+    splines are identical.  NADAVCA_FIT_WORKERS=0 disables the pool."""
+    global _FIT_POOL
+    import os
+    jobs = list(jobs)
+    if workers is None:
+        workers = int(os.environ.get('NADAVCA_FIT_WORKERS', min(32, max(1, (os.cpu_count() or 1) //
+                                                                        int(os.environ.get('LOCAL_WORLD_SIZE', '1'))))))
+    if workers <= 1 or len(jobs) < 32:
+        return _Ready([fit_spline(*job) for job in jobs])
+    if _FIT_POOL is None or _FIT_POOL[1] != workers:
+        import atexit
+        import multiprocessing
+        if _FIT_POOL is not None:
+            _FIT_POOL[0].terminate()
+        pool = multiprocessing.get_context('forkserver').Pool(workers)
+        atexit.register(pool.terminate)
+        _FIT_POOL = (pool, workers)
+    return _FIT_POOL[0].map_async(_fit_spline_job, jobs, chunksize=max(1, len(jobs) // (4 * workers)))
+
+
+def _normalize_on_device(values, device, process_group=None):
+    """clip((values - median) / MAD, -5, 5) computed on CUDA device `device` (csrc/select.cu); `values` is this
+    rank's share of the pooled samples."""
+    import ctypes
+    import torch
+    from . import _cabi
+    lib = _cabi.require_device()
+    dev = torch.device('cuda', device)
+    stream = torch.cuda.current_stream(dev)
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    d_values = torch.from_numpy(numpy.ascontiguousarray(values, dtype=numpy.float64)).to(dev)
+    n_local = d_values.numel()
+    dist = None
+    if process_group is not None:
+        import torch.distributed as dist
+    count = torch.tensor([n_local], dtype=torch.int64, device=dev)
+    if dist is not None:
+        dist.all_reduce(count, group=process_group)
+    n = int(count.item())
+    if n == 0:
+        return numpy.zeros(0)
+
+    def kth(k, absolute_deviation, shift):
+        """k-th smallest (0-based) pooled value: most significant digit first, 8 bits per pass."""
+        prefix = 0
+        for fixed in range(0, 64, 8):
+            hist = torch.zeros(256, dtype=torch.int64, device=dev)
+            _cabi.check(lib.nvb_radix_histogram_d(device, ctypes.c_void_p(d_values.data_ptr()), n_local,
+                                                  int(absolute_deviation), float(shift), prefix, fixed,
+                                                  ctypes.c_void_p(hist.data_ptr()), sp), 'nvb_radix_histogram_d')
+            if dist is not None:
+                dist.all_reduce(hist, group=process_group)
+            cum = numpy.cumsum(hist.cpu().numpy())
+            digit = int(numpy.searchsorted(cum, k, side='right'))
+            if digit:
+                k -= int(cum[digit - 1])
+            prefix = (prefix << 8) | digit
+        return _key_to_float(prefix)
+
+    def median(absolute_deviation, shift):
+        if n % 2:
+            return kth(n // 2, absolute_deviation, shift)
+        return (kth(n // 2 - 1, absolute_deviation, shift) + kth(n // 2, absolute_deviation, shift)) / 2.0
+
+    shift = median(False, 0.0)
+    scale = median(True, shift)
+    d_out = torch.empty_like(d_values)
+    _cabi.check(lib.nvb_normalize_clip_d(device, ctypes.c_void_p(d_values.data_ptr()), n_local, shift, scale, -5.0, 5.0,
+                                         ctypes.c_void_p(d_out.data_ptr()), sp), 'nvb_normalize_clip_d')
+    return d_out.cpu().numpy()
 
 
 def _ordered_keys(values):

@@ -426,3 +426,25 @@ def test_meth_scores_on_gpu_alignments_match_reference_golden(golden_estimator, 
         assert [maxs3(f[2]) for f in feats] == g['meth/read%d/aggregated' % i].tolist()
         total += len(feats)
     assert total >= 10
+
+
+@pytest.mark.parametrize('n_reads', [1, 4, 7])
+def test_device_normalisation_equals_numpy_bit_for_bit(lib_built, n_reads):
+    """Read.normalize_reads(device=...) == the host path (numpy.median twice + clip, read.py:67-81): exact radix
+    select on the GPU, odd and even pooled counts, repeated values around the medians, integer raw signals."""
+    from nadavca_b200.read import Read
+    rng = np.random.default_rng(200 + n_reads)
+    raws = []
+    for i in range(n_reads):
+        n = int(rng.integers(50, 4000)) + (i == 0)
+        raw = np.round(rng.normal(90, 15, size=n) * 4) / 4.0          # many ties
+        raw[rng.integers(0, n, size=5)] = rng.choice([-300.0, 800.0], size=5)  # outliers beyond the clip
+        raws.append(raw.astype(np.int16) if i % 3 == 2 else raw)
+    host = [Read.from_arrays(r, 'ACGT', {0: 0}) for r in raws]
+    gpu = [Read.from_arrays(r, 'ACGT', {0: 0}) for r in raws]
+    Read.normalize_reads(host)
+    Read.normalize_reads(gpu, device=0)
+    for a, b in zip(host, gpu):
+        assert b.normalized_signal.dtype == np.float64
+        assert np.array_equal(a.normalized_signal, b.normalized_signal)
+    assert max(abs(b.normalized_signal).max() for b in gpu) == 5.0

@@ -296,3 +296,39 @@ def test_output_writers_keep_the_reference_layout(tmp_path):
     assert lines[2].startswith('3\tT\t1\t1.0000000000000000\t0.0000000000000000')
     output.write_snp_tables([chunk, None], 'ACGTACGT', str(tmp_path / 'ind'), independent=True, names=['a.fast5', 'b'])
     assert sorted(os.listdir(tmp_path / 'ind')) == ['a.txt']
+
+
+def test_linear_fit_equals_scipy_linregress():
+    """align_signal's fast slope / intercept == scipy.stats.linregress bit for bit (align_signal.py:73)."""
+    from scipy.stats import linregress
+    from nadavca_b200.align_signal import linear_fit
+    rng = np.random.default_rng(17)
+    for n in (2, 3, 17, 500, 2000, 2311):
+        x = rng.normal(0, 1.3, size=n)
+        y = 0.93 * x + 0.07 + rng.normal(0, 0.2, size=n)
+        want = linregress(x, y)
+        slope, intercept = linear_fit(x, list(y))
+        assert slope == want.slope and intercept == want.intercept, n
+    with_nan = np.array([0.1, np.nan, 0.5])
+    s, i = linear_fit(np.array([0.0, 1.0, 2.0]), with_nan)
+    assert np.isnan(s) and np.isnan(i)
+
+
+def test_fit_splines_pool_equals_inline(golden_estimator):
+    """The worker-process pool of the spline fits returns exactly what the inline scipy call returns."""
+    from nadavca_b200.read import fit_spline, fit_splines_async
+    rng = np.random.default_rng(23)
+    jobs = []
+    for i in range(40):
+        n = int(rng.integers(30, 200))
+        expected = rng.normal(0, 1.2, size=n)
+        means = expected + rng.normal(0, 0.15, size=n)
+        means[::17] += 3.0  # dropped by the |expected - mean| <= 1 filter
+        jobs.append((means, expected))
+    inline = [fit_spline(*j) for j in jobs]
+    pooled = fit_splines_async(jobs, workers=3).get()
+    few = fit_splines_async(jobs[:5], workers=3).get()
+    for a, b in zip(inline, pooled):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+    for a, b in zip(inline, few):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
