@@ -137,6 +137,177 @@ __device__ __forceinline__ void xd_renorm(XD &v) {
   }
 }
 
+// ---- signal staging: a per-warp ring in shared memory, filled by 1-D TMA bulk copies -------------------------------
+// A sweep warp reads, at every step, one sample per lane out of a window of at most 64 consecutive samples that slides
+// by (at most) one sample per step.  Fetching them with per-lane loads put the global-load latency on the critical
+// path of every step (ncu, profiles/r01e: 27 % of the stall samples of the hot loop were the first use of that
+// load).  Instead the warp keeps NS = 4 or 8 chunks of 32 samples in shared memory: chunk k holds the samples with
+// ABSOLUTE index [32k, 32k+32) of the batch's signal array (absolute, so that every chunk starts on a 256-byte
+// boundary of the allocation: cp.async.bulk needs 16-byte alignment and read slices start anywhere), one elected lane
+// issues cp.async.bulk (global -> shared, completion on an mbarrier) a few dozen steps before the window reaches the
+// chunk, and the warp waits on the mbarrier only when it first needs it.
+// Bookkeeping of a ring; lives in shared memory next to the ring (it is touched only every few steps, by the whole
+// warp with uniform values, and must not cost registers in the step loop).
+struct RingState {
+  const double *base;       // signal array, rounded down to a 256-sample boundary in front of the read's slice
+  int limit;                // chunks at or beyond this id lie outside the allocation
+  int issued_lo, issued_hi; // chunk ids (relative to `base`) issued so far: [issued_lo, issued_hi]; empty when lo > hi
+  int ready_lo, ready_hi;   // ... and known to have landed
+  unsigned phases;          // bit q: parity the NEXT copy into slot q completes
+  int pad;
+};
+// NS slots of 32 samples, NS mbarriers, the state: NS = 8 for the rotating sweep (window of up to 64 samples), 4 for the
+// striped sweep (window of 32)
+constexpr int ring_bytes(int NS) { return NS * 256 + NS * 8 + (int)sizeof(RingState); }
+
+template <int NS>
+struct SignalRing {
+  unsigned buf;  // shared-memory address of the NS * 32 samples; the NS mbarriers and the RingState follow
+  int off;       // index of the read's sample 0 relative to RingState::base (0..255)
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <int NS>
+__device__ __forceinline__ RingState *ring_state(const SignalRing<NS> &R) {
+  return reinterpret_cast<RingState *>(__cvta_shared_to_generic(R.buf + NS * 256 + NS * 8));
+}
+
+// `mem` = ring_bytes(NS) of 16-byte aligned shared memory owned by this warp, `signal` = the batch's signal array
+// (256-byte aligned allocation of `total` samples), `first` = absolute index of the read's sample 0.
+template <int NS>
+__device__ __forceinline__ void ring_init(SignalRing<NS> &R, void *mem, const double *signal, long long first,
+                                          long long total, int lane) {
+  const long long aligned = first & ~255LL;
+  R.buf = smem_u32(mem);
+  R.off = (int)(first - aligned);
+  if (lane < NS) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(R.buf + NS * 256 + lane * 8));
+  if (lane == 0) {
+    RingState *S = ring_state(R);
+    const long long chunks = (total - aligned + 31) >> 5;
+    S->base = signal + aligned;
+    S->limit = (int)(chunks < 0x7fffffff ? chunks : 0x7fffffff);
+    S->issued_lo = 1; S->issued_hi = 0; S->ready_lo = 1; S->ready_hi = 0;
+    S->phases = 0;
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+}
+
+// Lane 0 issues the bulk copy of chunk `k` into its ring slot (256 bytes, both addresses 256-byte aligned) and flips
+// the slot's phase bit.
+template <int NS>
+__device__ __forceinline__ void ring_issue(const SignalRing<NS> &R, RingState *S, int k) {
+  if (k < 0 || k >= S->limit) return;
+  const unsigned slot = (unsigned)k & (unsigned)(NS - 1);
+  S->phases ^= 1u << slot;
+  const unsigned bar = R.buf + NS * 256 + slot * 8, dst = R.buf + slot * 256;
+  // the slot was last read through the generic proxy: order those reads before the async-proxy write
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 256;" ::"r"(bar) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 256, [%2];"
+               ::"r"(dst), "l"(S->base + (long long)k * 32), "r"(bar) : "memory");
+}
+
+// All lanes wait until the latest copy into chunk k's slot has landed (at most one copy per slot is in flight: a slot
+// is reused NS chunks later, long after its previous chunk was waited for).
+template <int NS>
+__device__ __forceinline__ void ring_wait(const SignalRing<NS> &R, int k, int limit, unsigned phases) {
+  if (k < 0 || k >= limit) return;
+  const unsigned slot = (unsigned)k & (unsigned)(NS - 1);
+  const unsigned bar = R.buf + NS * 256 + slot * 8, parity = ((phases >> slot) & 1u) ^ 1u;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "RING_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra RING_DONE;\n"
+      "bra RING_WAIT;\n"
+      "RING_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// Keep the ring ahead of the window.  Called by the whole warp with warp-uniform arguments (sample indices of the read,
+// clamped by the caller to [0, N-1]): the steps until the next call read samples [need_lo, need_hi]; samples
+// [ahead_lo, ahead_hi] (a superset, fewer than (NS - 1) * 32 samples) are to be in flight.  A forward sweep (REV = false) only
+// ever extends the ring upwards after its first call, a reverse sweep only downwards: callers keep one chunk of
+// slack on the trailing side so that the small backward wobbles of the window never reach below what is resident.
+template <int NS>
+__device__ __forceinline__ void ring_reset(const SignalRing<NS> &R, int lane);
+
+template <bool REV, int NS>
+__device__ __forceinline__ void ring_advance(const SignalRing<NS> &R, int need_lo, int need_hi, int ahead_lo, int ahead_hi,
+                                             int lane) {
+  RingState *S = ring_state(R);
+  const int nl = (R.off + need_lo) >> 5, nh = (R.off + need_hi) >> 5;
+  const int al = (R.off + ahead_lo) >> 5, ah = (R.off + ahead_hi) >> 5;
+  bool first = S->issued_lo > S->issued_hi;
+  // a window that jumped by a whole ring (it never does in the sweeps as they are) starts over instead of queueing
+  // several copies on one slot's mbarrier
+  if (!first && (REV ? (S->issued_lo - al >= NS) : (ah - S->issued_hi >= NS))) {
+    ring_reset(R, lane);
+    first = true;
+  }
+  if (first || (!REV ? (ah > S->issued_hi) : (al < S->issued_lo))) {
+    __syncwarp();  // every lane is done reading the slots that are about to be overwritten (and the state)
+    if (lane == 0) {
+      if (first) {  // the initial fill
+        if (!REV) { S->issued_lo = al; S->issued_hi = al - 1; S->ready_lo = al; S->ready_hi = al - 1; }
+        else { S->issued_hi = ah; S->issued_lo = ah + 1; S->ready_hi = ah; S->ready_lo = ah + 1; }
+      }
+      if (!REV) while (S->issued_hi < ah) ring_issue(R, S, ++S->issued_hi);
+      else while (S->issued_lo > al) ring_issue(R, S, --S->issued_lo);
+    }
+    __syncwarp();
+  }
+  const int limit = S->limit;
+  const unsigned phases = S->phases;
+  if (!REV) {
+    int r = S->ready_hi;
+    if (r < nh) {
+      while (r < nh) ring_wait(R, ++r, limit, phases);
+      __syncwarp();
+      if (lane == 0) S->ready_hi = r;
+    }
+  } else {
+    int r = S->ready_lo;
+    if (r > nl) {
+      while (r > nl) ring_wait(R, --r, limit, phases);
+      __syncwarp();
+      if (lane == 0) S->ready_lo = r;
+    }
+  }
+}
+
+// Before the warp exits: no bulk copy may still be in flight towards its shared memory.  Waits for the latest copy
+// into each of the 8 slots (a slot that was never used reports completion at once).
+template <int NS>
+__device__ __forceinline__ void ring_drain(const SignalRing<NS> &R) {
+  __syncwarp();
+  const unsigned phases = ring_state(R)->phases;
+#pragma unroll 1
+  for (int slot = 0; slot < NS; slot++) ring_wait(R, slot, NS, phases);
+}
+
+// Forget what is resident (after draining): the next ring_advance starts with an initial fill.  For sweeps whose
+// window jumps (every stripe of the striped sweep starts at its own band start).
+template <int NS>
+__device__ __forceinline__ void ring_reset(const SignalRing<NS> &R, int lane) {
+  ring_drain(R);
+  if (lane == 0) {
+    RingState *S = ring_state(R);
+    S->issued_lo = 1; S->issued_hi = 0; S->ready_lo = 1; S->ready_hi = 0;
+  }
+  __syncwarp();
+}
+
+// Sample i of the read (its chunk must be resident).
+template <int NS>
+__device__ __forceinline__ double ring_read(const SignalRing<NS> &R, int i) {
+  double x;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(R.buf + (((R.off + i) & (NS * 32 - 1)) << 3)));
+  return x;
+}
+
 enum { NVB_ROLE_IDLE = 0, NVB_ROLE_LOADER = 1, NVB_ROLE_PAIR = 2, NVB_ROLE_JOIN = 3 };
 
 // Per-lane constants of one stripe / task.
@@ -191,15 +362,31 @@ struct LaneOut {
 // FWD_ONLY (forward-only callers with wobble rows): the A-row needs only its upper band limit (below the band its
 // inflow is already zero) and the B-row output only its lower one (above the band the consumer's own A-row limit cuts
 // it off); lanes without an output use ms = INT_MAX.  Measured neutral on the SNP kernel, so currently unused.
-template <int MEL, int MODE, bool WITH_JOIN, int PH, bool FWD_ONLY>
-__device__ __forceinline__ void lane_step(const LaneCfg &L, LaneState<MEL> &S, int c, double x, const LaneOut &in,
-                                          double sF, int sX, LaneOut &out, XD &aout) {
+// The step comes in two halves so that the latency-bound sweeps can evaluate the emission of step t+1 (which depends
+// on nothing but the sample) while the state update of step t waits for its neighbour: lane_emit + lane_update.
+__device__ __forceinline__ void lane_emit(const LaneCfg &L, double x, double &p, int &kk) {
   // own emission, reference formula ac - d*d*mc (kmer_model.cpp:47-51)
   const double d = x - L.mu;
   const double l = L.ac - d * d * L.mc;
+  exp_ext(l, p, kk);
+}
+
+template <int MEL, int MODE, bool WITH_JOIN, int PH, bool FWD_ONLY>
+__device__ __forceinline__ void lane_update(const LaneCfg &L, LaneState<MEL> &S, int c, double p, int kk,
+                                            const LaneOut &in, double sF, int sX, LaneOut &out, XD &aout);
+
+template <int MEL, int MODE, bool WITH_JOIN, int PH, bool FWD_ONLY>
+__device__ __forceinline__ void lane_step(const LaneCfg &L, LaneState<MEL> &S, int c, double x, const LaneOut &in,
+                                          double sF, int sX, LaneOut &out, XD &aout) {
   double p;
   int kk;
-  exp_ext(l, p, kk);
+  lane_emit(L, x, p, kk);
+  lane_update<MEL, MODE, WITH_JOIN, PH, FWD_ONLY>(L, S, c, p, kk, in, sF, sX, out, aout);
+}
+
+template <int MEL, int MODE, bool WITH_JOIN, int PH, bool FWD_ONLY>
+__device__ __forceinline__ void lane_update(const LaneCfg &L, LaneState<MEL> &S, int c, double p, int kk,
+                                            const LaneOut &in, double sF, int sX, LaneOut &out, XD &aout) {
   out.p = p;
   out.k = kk;
 

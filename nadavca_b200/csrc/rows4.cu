@@ -68,6 +68,7 @@ struct StoreTile {
   RowMeta *meta;  // [32]
 };
 constexpr size_t kTileBytes = 32 * TSTRIDE * (sizeof(double) + sizeof(int32_t)) + 32 * sizeof(RowMeta);
+constexpr size_t kRingStride = (ring_bytes(4) + 15) / 16 * 16;  // per-warp signal ring (dp3.cuh)
 
 // Write the first `cnt` steps (t0 .. t0+cnt-1) of a tile to the matrix planes.
 template <bool REV>
@@ -99,7 +100,7 @@ struct Handoff {
 
 template <int MEL, int MODE, bool REV>
 __device__ __forceinline__ void sweep_stripes(const ModelDev &M, const ReadView &v, double *F, int32_t *X, int lane, int warp, int NW,
-                              const Handoff &H, const StoreTile &tileB, const StoreTile &tileA) {
+                              const Handoff &H, const StoreTile &tileB, const StoreTile &tileA, const SignalRing<4> &R) {
   constexpr int mode = MODE;
   const int n = v.n, N = v.N;
   const double C_E2 = 0.1353352832366127;  // exp(-2): the "/ 2" of kmer_model.cpp:60 is "- 2.0" in log space
@@ -186,7 +187,17 @@ __device__ __forceinline__ void sweep_stripes(const ModelDev &M, const ReadView 
       const int c = REV ? C0 - (t - lane) : C0 + (t - lane);
       return min(max(REV ? c : c - 1, 0), N - 1);
     };
-    double x0 = __ldg(v.sig + sample_index(0)), x1 = __ldg(v.sig + sample_index(1));
+    // signal window of the warp (dp3.cuh): 32 consecutive samples sliding by one per step, staged by TMA bulk copies
+    auto stage = [&](int t) {  // the steps t .. t+TS read (and evaluate one step ahead) these samples
+      const int lo = REV ? C0 - t - TS : C0 + t - NVB_WARP, hi = REV ? C0 - t + NVB_WARP - 1 : C0 + t + TS - 1;
+      ring_advance<REV, 4>(R, min(max(lo, 0), N - 1), min(max(hi, 0), N - 1), min(max(lo - (REV ? 32 : 8), 0), N - 1),
+                           min(max(hi + (REV ? 8 : 32), 0), N - 1), lane);
+    };
+    ring_reset(R, lane);  // every stripe starts at its own band start
+    stage(0);
+    double p_cur;
+    int k_cur;
+    lane_emit(L, ring_read(R, sample_index(0)), p_cur, k_cur);  // emissions are evaluated one step ahead
     unsigned ready = 0;  // cells of the hand-off row known to be ready (sweep order)
     const unsigned row_cells = (unsigned)(le - ls + 1);
     for (int t = 0; t < T; t++) {
@@ -205,13 +216,15 @@ __device__ __forceinline__ void sweep_stripes(const ModelDev &M, const ReadView 
         }
       }
       const int c = REV ? C0 - (t - lane) : C0 + (t - lane);
-      // the sample of step t was requested two steps ago (ncu: the warp otherwise waits for this load every step)
-      const double x = x0;
-      x0 = x1;
-      x1 = __ldg(v.sig + sample_index(t + 2));
+      if ((t & (TS - 1)) == 0 && t > 0) stage(t);
+      // the emission of step t+1 needs only its sample: it overlaps the state update of step t, which waits for the
+      // neighbour's shuffle
+      const double p = p_cur;
+      const int kk = k_cur;
+      lane_emit(L, ring_read(R, sample_index(t + 1)), p_cur, k_cur);
       LaneOut in = shfl_up_out<MODE>(out);
       XD aout;
-      lane_step<MEL, MODE, false, -1, false>(L, S, c, x, in, 1.0, 0, out, aout);
+      lane_update<MEL, MODE, false, -1, false>(L, S, c, p, kk, in, 1.0, 0, out, aout);
       if (lane == 0) {
         const bool inb = (c >= L.ms && c <= L.me);
         out.f = inb ? 1.0 : 0.0;
@@ -252,6 +265,7 @@ __device__ __forceinline__ void sweep_stripes(const ModelDev &M, const ReadView 
     }
     __syncwarp();
   }
+  ring_drain(R);
 }
 
 template <int MEL, int MODE>
@@ -293,12 +307,17 @@ __global__ void __launch_bounds__(224, 4) sweep4_kernel(ModelDev M, BatchDev B, 
   };
   constexpr int TPW = (MODE == NVB_MODE_TRANS) ? 2 : 1;  // tiles per warp: B rows, plus A rows for the transition sweep
   const StoreTile tileB = make_tile(TPW * warp), tileA = make_tile(TPW * warp + TPW - 1);
+  // per-warp signal ring (4 chunks of 32 samples + mbarriers + state) behind the tiles
+  SignalRing<4> R;
+  unsigned char *rings = tiles + (size_t)TPW * NW * kTileBytes;
+  rings += (16 - (smem_u32(rings) & 15u)) & 15u;  // cp.async.bulk needs a 16-byte aligned destination
+  ring_init(R, rings + (size_t)warp * kRingStride, B.signal, B.sig_off[b], B.sig_off[B.n_reads], lane);
   if (threadIdx.x < H.nb) H.word[threadIdx.x] = 0ull;
   __syncthreads();
   ReadView v = read_view(B, b);
   const int64_t base = mat_base[b];
-  if (item & 1) sweep_stripes<MEL, MODE, true>(M, v, sF + base, sX + base, lane, warp, NW, H, tileB, tileA);
-  else sweep_stripes<MEL, MODE, false>(M, v, pF + base, pX + base, lane, warp, NW, H, tileB, tileA);
+  if (item & 1) sweep_stripes<MEL, MODE, true>(M, v, sF + base, sX + base, lane, warp, NW, H, tileB, tileA, R);
+  else sweep_stripes<MEL, MODE, false>(M, v, pF + base, pX + base, lane, warp, NW, H, tileB, tileA, R);
 }
 
 // Node::TotalLikelihood(prefix[n], suffix[n]) (dtw.cpp:83-85); suffix[n] is all ones.  Two passes over the row:
@@ -370,7 +389,7 @@ SweepPlan plan_sweep(int mode, int wave_maxw, int force_warps) {
   NW = NW < 1 ? 1 : (NW > 7 ? 7 : NW);
   if (force_warps > 0) NW = force_warps > 7 ? 7 : force_warps;  // experiments (NVB_SWEEP_WARPS, read at load)
   const int tiles_per_warp = (mode == NVB_MODE_TRANS) ? 2 : 1;
-  auto tile_bytes = [&](int nw) { return (size_t)64 + (size_t)tiles_per_warp * nw * kTileBytes; };
+  auto tile_bytes = [&](int nw) { return (size_t)64 + 16 + (size_t)nw * (tiles_per_warp * kTileBytes + kRingStride); };
   auto bytes = [&](int nw) { return tile_bytes(nw) + (size_t)(nw + 1) * p.width * (sizeof(double) + sizeof(int32_t)); };
   const size_t limit = 200 * 1024;
   p.global_handoff = bytes(1) > limit;  // not even two hand-off rows fit (band rows beyond ~8.5k columns)

@@ -38,6 +38,7 @@ struct StoreTile {
   RowMeta *meta;  // [32]
 };
 constexpr size_t kTileBytes = 32 * TSTRIDE * (sizeof(double) + sizeof(int32_t)) + 32 * sizeof(RowMeta);
+constexpr size_t kWarpBytes = ((4 * kTileBytes + ring_bytes(8) + 255) / 256) * 256;  // keeps every ring 256-byte aligned
 
 template <bool REV>
 __device__ __forceinline__ void flush_tile(const StoreTile &tile, double *F, int32_t *X, int C0, int t0, int lane) {
@@ -68,7 +69,8 @@ struct Slot {
   int t_end;        // last step with an in-band column
   long long boff, aoff;
   int ws, awe;      // A-row band for the stores of the transition sweep (empty when nothing is stored)
-  double x_next;    // signal sample of the next step, requested one step ahead
+  double p_cur;     // emission of the NEXT step to run, evaluated one step ahead (lane_emit): p_cur * 2^k_cur
+  int k_cur;
 };
 
 template <int MEL>
@@ -77,7 +79,7 @@ __device__ __forceinline__ void slot_clear(Slot<MEL> &Q) {
   lane_reset(Q.S);
   Q.out.f = 0.0; Q.out.E = NVB_EZERO; Q.out.p = 1.0; Q.out.k = 0;
   Q.aout = xd_zero();
-  Q.pair = -1; Q.t_end = -1; Q.boff = 0; Q.aoff = 0; Q.ws = 1; Q.awe = 0; Q.x_next = 0.0;
+  Q.pair = -1; Q.t_end = -1; Q.boff = 0; Q.aoff = 0; Q.ws = 1; Q.awe = 0; Q.p_cur = 1.0; Q.k_cur = 0;
 }
 
 template <bool REV>
@@ -102,14 +104,14 @@ __device__ __forceinline__ int sample_index(const ReadView &v, int C0, int g, in
 }
 
 template <int MEL, int MODE, bool REV>
-__device__ __forceinline__ void slot_start(Slot<MEL> &Q, const ModelDev &M, const ReadView &v, int C0, int g, int t) {
+__device__ __forceinline__ void slot_start(Slot<MEL> &Q, const ModelDev &M, const ReadView &v, const SignalRing<8> &R,
+                                           int C0, int g, int t) {
   const int n = v.n;
   const int i = pair_base<REV>(n, g);
   const double C_E2 = 0.1353352832366127;  // exp(-2): the "/ 2" of kmer_model.cpp:60 is "- 2.0" in log space
   slot_clear(Q);
   Q.pair = g;
   Q.t_end = pair_t_end<REV>(v, C0, g);
-  Q.x_next = __ldg(v.sig + sample_index<REV>(v, C0, g, t));
   const bool hasA = (MODE != NVB_MODE_PLAIN) && (REV ? (i <= n - 2) : (i >= 1));
   const int aband = REV ? i + 1 : i, bband = REV ? i : i + 1, nb = REV ? i + 1 : i - 1;
   const int id = kmer_id(M, v, i, INT32_MIN, 0);
@@ -134,16 +136,21 @@ __device__ __forceinline__ void slot_start(Slot<MEL> &Q, const ModelDev &M, cons
       Q.L.cm = C_E2; Q.L.abias = 0;
     }
   }
+  lane_emit(Q.L, ring_read(R, sample_index<REV>(v, C0, g, t)), Q.p_cur, Q.k_cur);  // emission of its first step
 }
 
 // One step of one slot.  `pf .. pk, ptag` = outputs of the producer lane's slot(s) at the previous step.
 template <int MEL, int MODE, bool REV>
-__device__ __forceinline__ void slot_step(Slot<MEL> &Q, const ReadView &v, int C0, int t, const LaneOut &in0, int tag0,
-                                          const LaneOut &in1, int tag1, bool have1, int ones_s, int ones_e) {
+__device__ __forceinline__ void slot_step(Slot<MEL> &Q, const ReadView &v, const SignalRing<8> &R, int C0, int t,
+                                          const LaneOut &in0, int tag0, const LaneOut &in1, int tag1, bool have1,
+                                          int ones_s, int ones_e) {
   const int g = Q.pair;
   const int c = REV ? C0 - (t - g) : C0 + (t - g);
-  const double x = Q.x_next;
-  Q.x_next = __ldg(v.sig + sample_index<REV>(v, C0, g, t + 1));
+  // the emission of step t+1 depends on nothing but its sample (staged in shared memory): it is evaluated here,
+  // independently of the state update of step t below, so that the two dependency chains overlap
+  const double p = Q.p_cur;
+  const int kk = Q.k_cur;
+  lane_emit(Q.L, ring_read(R, sample_index<REV>(v, C0, g, t + 1)), Q.p_cur, Q.k_cur);
   LaneOut in;
   const int want = g - 1;
   if (g == 0) {  // the all-ones initial row (dtw.cpp:50,66,182,190)
@@ -156,7 +163,7 @@ __device__ __forceinline__ void slot_step(Slot<MEL> &Q, const ReadView &v, int C
   } else {  // the producer has left its band: nothing flows any more
     in.f = 0.0; in.E = NVB_EZERO; in.p = 1.0; in.k = 0;
   }
-  lane_step<MEL, MODE, false, -1, false>(Q.L, Q.S, c, x, in, 1.0, 0, Q.out, Q.aout);
+  lane_update<MEL, MODE, false, -1, false>(Q.L, Q.S, c, p, kk, in, 1.0, 0, Q.out, Q.aout);
 }
 
 template <int MODE>
@@ -188,7 +195,7 @@ __device__ __forceinline__ void write_meta(const StoreTile &tb, const StoreTile 
 
 template <int MEL, int MODE, bool REV>
 __device__ void sweep_rotate(const ModelDev &M, const ReadView &v, double *F, int32_t *X, int lane,
-                             const StoreTile (&tiles)[4]) {
+                             const StoreTile (&tiles)[4], const SignalRing<8> &R) {
   const int n = v.n;
   constexpr bool TRANS = (MODE == NVB_MODE_TRANS);
   const StoreTile &tPB = tiles[0], &tPA = tiles[1], &tSB = tiles[2], &tSA = tiles[3];
@@ -217,9 +224,28 @@ __device__ void sweep_rotate(const ModelDev &M, const ReadView &v, double *F, in
       if (P.pair >= 0 && t >= P.t_end + 2) {
         if (Q2.pair >= 0) { P = Q2; slot_clear(Q2); } else slot_clear(P);
       }
-      if (next_start < t + TS) {  // its first in-band column falls into this tile
-        if (P.pair < 0) slot_start<MEL, MODE, REV>(P, M, v, C0, next_g, t);
-        else slot_start<MEL, MODE, REV>(Q2, M, v, C0, next_g, t);  // the band kernel guarantees Q2 is free
+      const bool starting = next_start < t + TS;  // its first in-band column falls into this tile
+      {
+        // signal window of this tile: the samples the live pairs (and the one starting now) read at steps t .. t+TS
+        // (the last step evaluates the emission of step t+TS), plus what to have in flight beyond it
+        int glo = 0x7fffffff, ghi = -1;
+        if (P.pair >= 0) { glo = min(glo, P.pair); ghi = max(ghi, P.pair); }
+        if (Q2.pair >= 0) { glo = min(glo, Q2.pair); ghi = max(ghi, Q2.pair); }
+        if (starting) { glo = min(glo, next_g); ghi = max(ghi, next_g); }
+        glo = __reduce_min_sync(NVB_FULL, glo);
+        ghi = __reduce_max_sync(NVB_FULL, ghi);
+        if (ghi >= 0) {
+          const int last = v.N - 1;
+          const int lo = REV ? C0 - t - TS + glo : C0 + t - ghi - 1;
+          const int hi = REV ? C0 - t + ghi : C0 + t + TS - glo - 1;
+          const int need_lo = min(max(lo, 0), last), need_hi = min(max(hi, 0), last);
+          const int ahead_lo = min(max(lo - (REV ? 48 : 32), 0), last), ahead_hi = min(max(hi + (REV ? 32 : 48), 0), last);
+          ring_advance<REV, 8>(R, need_lo, need_hi, ahead_lo, ahead_hi, lane);
+        }
+      }
+      if (starting) {
+        if (P.pair < 0) slot_start<MEL, MODE, REV>(P, M, v, R, C0, next_g, t);
+        else slot_start<MEL, MODE, REV>(Q2, M, v, R, C0, next_g, t);  // the band kernel guarantees Q2 is free
         next_g += NVB_WARP;
         next_start = (next_g < n) ? pair_t_start<REV>(v, C0, next_g) : 0x7fffffff;
       }
@@ -241,12 +267,12 @@ __device__ void sweep_rotate(const ModelDev &M, const ReadView &v, double *F, in
     }
     // ---- the step(s) ------------------------------------------------------------------------------------------------
     const int k = t & (TS - 1);
-    if (P.pair >= 0) slot_step<MEL, MODE, REV>(P, v, C0, t, in0, tag0, in1, tag1, any2_tile, ones_s, ones_e);
+    if (P.pair >= 0) slot_step<MEL, MODE, REV>(P, v, R, C0, t, in0, tag0, in1, tag1, any2_tile, ones_s, ones_e);
     tPB.f[lane * TSTRIDE + k] = P.out.f;
     tPB.x[lane * TSTRIDE + k] = P.out.E;
     if (TRANS) { tPA.f[lane * TSTRIDE + k] = P.aout.f; tPA.x[lane * TSTRIDE + k] = P.aout.e; }
     if (any2_tile) {
-      if (Q2.pair >= 0) slot_step<MEL, MODE, REV>(Q2, v, C0, t, in0, tag0, in1, tag1, true, ones_s, ones_e);
+      if (Q2.pair >= 0) slot_step<MEL, MODE, REV>(Q2, v, R, C0, t, in0, tag0, in1, tag1, true, ones_s, ones_e);
       tSB.f[lane * TSTRIDE + k] = Q2.out.f;
       tSB.x[lane * TSTRIDE + k] = Q2.out.E;
       if (TRANS) { tSA.f[lane * TSTRIDE + k] = Q2.aout.f; tSA.x[lane * TSTRIDE + k] = Q2.aout.e; }
@@ -266,6 +292,7 @@ __device__ void sweep_rotate(const ModelDev &M, const ReadView &v, double *F, in
       if (any2_tile) lane_renorm(Q2.S);
     }
   }
+  ring_drain(R);
 }
 
 template <int MEL, int MODE>
@@ -279,7 +306,7 @@ __global__ void __launch_bounds__(64, NVB_ROT_MIN_BLOCKS) sweep5_kernel(ModelDev
   if (item >= n_items) return;
   const int b = b0 + (item >> 1);
   if (B.flags[b] != 0) return;  // bad band
-  unsigned char *base = reinterpret_cast<unsigned char *>(smem_raw) + (size_t)warp * 4 * kTileBytes;
+  unsigned char *base = reinterpret_cast<unsigned char *>(smem_raw) + (size_t)warp * kWarpBytes;
   StoreTile tiles[4];
 #pragma unroll
   for (int i = 0; i < 4; i++) {
@@ -290,15 +317,18 @@ __global__ void __launch_bounds__(64, NVB_ROT_MIN_BLOCKS) sweep5_kernel(ModelDev
   }
   ReadView v = read_view(B, b);
   const int64_t mb = mat_base[b];
-  if (item & 1) sweep_rotate<MEL, MODE, true>(M, v, sF + mb, sX + mb, lane, tiles);
-  else sweep_rotate<MEL, MODE, false>(M, v, pF + mb, pX + mb, lane, tiles);
+  // signal ring (dp3.cuh) behind the four store tiles: 8 chunks of 32 samples + 8 mbarriers, filled by TMA bulk copies
+  SignalRing<8> R;
+  ring_init(R, base + 4 * kTileBytes, B.signal, B.sig_off[b], B.sig_off[B.n_reads], lane);
+  if (item & 1) sweep_rotate<MEL, MODE, true>(M, v, sF + mb, sX + mb, lane, tiles, R);
+  else sweep_rotate<MEL, MODE, false>(M, v, pF + mb, pX + mb, lane, tiles, R);
 }
 
 template <int MEL, int MODE>
 void launch_mode(const ModelDev &M, const BatchDev &B, int b0, int n_items, const int64_t *mb, double *pF, int32_t *pX,
                  double *sF, int32_t *sX, cudaStream_t st) {
-  const int warps = 2;  // 2 x 4 tiles x 2.4 KB = 19 KB per CTA
-  const size_t smem = (size_t)warps * 4 * kTileBytes;
+  const int warps = 2;  // 2 x (4 tiles x 2.7 KB + 2 KB ring) = 26 KB per CTA
+  const size_t smem = (size_t)warps * kWarpBytes;
   sweep5_kernel<MEL, MODE><<<(n_items + warps - 1) / warps, warps * NVB_WARP, smem, st>>>(M, B, b0, n_items, mb, pF, pX,
                                                                                          sF, sX);
 }
