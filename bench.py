@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument('--sweep-bandwidths', default='50,100,150,250,400,650,1000', help='--config 4')
     ap.add_argument('--sweep-batches', default='1,8,64,512,4096', help='--config 4: reads per GPU')
     ap.add_argument('--genome', type=int, default=4_600_000, help='synthetic genome length (E. coli-sized: configs[2])')
+    ap.add_argument('--no-api', action='store_true', help='skip the public-API timing block')
     ap.add_argument('--no-consensus', action='store_true', help='skip the consensus-mode (configs[2]) step')
     ap.add_argument('--bandwidth', type=int, default=None, help='default 150 (400 for --config 3)')
     ap.add_argument('--cpu-sample', type=int, default=0, help='reads in the CPU sample (0 = one per host core)')
@@ -556,6 +557,36 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    # ---- the public API (what a user of the reference calls), host glue included -------------------------------------
+    # estimate_snps: pooled normalisation (device), aligner glue, packing, refine, spline fits (worker pool), SNP DP,
+    # posterior, Chunk objects.  align_signal: per-read normalisation, two alignment rounds with transitions, linear
+    # renormalisation.  Reported next to `e2e` (the C-ABI path both arms are compared on); raw samples per second.
+    api = None
+    if not args.no_api:
+        import nadavca_b200
+        from nadavca_b200 import synthetic
+        reads_api = [it['read'] for it in items]
+        aligner = synthetic.SyntheticAligner(genome)
+        raw_samples = float(sum(len(r.raw_signal) for r in reads_api))
+
+        def timed_call(fn):
+            fn()  # warm-up: worker pool, workspaces
+            barrier()
+            t0 = time.perf_counter()
+            out = fn()
+            barrier()
+            return time.perf_counter() - t0, out
+
+        snp_s, chunks = timed_call(lambda: nadavca_b200.estimate_snps(None, reads_api, reference=genome, config=cfg,
+                                                                      kmer_model=km, independent=True, aligner=aligner))
+        align_s, aligned = timed_call(lambda: list(nadavca_b200.align_signal(None, reads_api, config=cfg, kmer_model=km,
+                                                                             aligner=aligner, reference=genome)))
+        api = {'estimate_snps_s': reduce_over_ranks(snp_s, 'max', dev),
+               'align_signal_s': reduce_over_ranks(align_s, 'max', dev),
+               'raw_samples': reduce_over_ranks(raw_samples, 'sum', dev),
+               'chunks': len([c for c in chunks if c is not None]),
+               'aligned': sum(1 for _, res in aligned if res is not None)}
+
     # ---- reductions over ranks -----------------------------------------------------------------------------------
     ms_max = reduce_over_ranks(ms, 'max', dev)
     overlap_max = None if overlap_ms is None else reduce_over_ranks(overlap_ms, 'max', dev)
@@ -594,13 +625,19 @@ def run_ours(args):
                          'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': ncu_traffic(args.reads), 'peak_source': peak_src,
                          'launch_ms': snp_launch_ms, 'algorithmic_bytes_per_launch': snp_bytes_per_launch,
                          'note': 'the SNP kernel is instruction-issue / FP64-pipe bound, not HBM bound: see alu'},
-            'alu': {'kernel': 'snp3_kernel', 'dp_cells_per_sec': snp_cells_per_s,
-                    'fp64_fma_per_sec_measured': fma_rate,
-                    'cells_per_fma_slot': snp_cells_per_s / fma_rate if fma_rate else None},
+            'alu': alu_block(snp_cells_per_s, fma_rate, clocks.summary().get('sm_mhz')),
             'stage_ms_per_step': {'rows_refine': tn['rows'][0] / args.steps, 'path': tn['path'][0] / args.steps,
                                   'rows_estimate': tt['rows'][0] / args.steps, 'no_snp': tt['no_snp'][0] / args.steps,
                                   'snp': tt['snp'][0] / args.steps},
             'cells_per_step_per_gpu': cells,
+            'api': None if api is None else {
+                'estimate_snps': {'call': 'nadavca_b200.estimate_snps(reads, independent=True)',
+                                  'seconds': api['estimate_snps_s'], 'unit': 'raw samples/s',
+                                  'value': api['raw_samples'] / api['estimate_snps_s'], 'chunks': api['chunks']},
+                'align_signal': {'call': 'nadavca_b200.align_signal(reads)  (two alignment rounds, transitions)',
+                                 'seconds': api['align_signal_s'], 'unit': 'raw samples/s',
+                                 'value': api['raw_samples'] / api['align_signal_s'], 'aligned': api['aligned']},
+                'reads_per_gpu': args.reads},
             'consensus': None if consensus is None else dict(
                 consensus, value=samples_all / (consensus['ms_per_step'] * 1e-3), unit='samples/s',
                 bus_GBs=(consensus['bus_bytes_per_step'] / (consensus['exchange_ms_per_step'] * 1e-3) / 1e9
@@ -619,6 +656,29 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# Warp instructions of one wavefront step of snp3_kernel<2, WOBBLE> (4 tasks = 24 pair lanes = up to 48 cells, 41.6 on
+# average over the band edges), counted in the SASS of the shipped library (cuobjdump -sass, profiles/r02_snp3_sass.txt):
+# 108 on the main path + 48 of the renormalisation block every 8th step; 27 + 4/8 of them issue to the FP64 pipe.
+SNP_WARP_INSTR_PER_STEP = 108 + 48 / 8.0
+SNP_FP64_INSTR_PER_STEP = 27 + 4 / 8.0
+SNP_CELLS_PER_STEP = 41.6
+
+
+def alu_block(snp_cells_per_s, fma_rate, sm_mhz):
+    """The bound that matters for the dominant kernel: instruction issue and the FP64 pipe, not HBM.  A B200 SM issues
+    4 warp instructions per clock (one per scheduler); its FP64 pipe takes one warp instruction every two clocks per
+    scheduler (64 FMA lanes per SM: the rate nvb_measure_fp64_fma_rate measures live)."""
+    steps_per_s = snp_cells_per_s / SNP_CELLS_PER_STEP
+    fp64_peak = fma_rate / 32.0 if fma_rate else None             # warp-level FP64 instructions per second
+    issue_peak = 148 * 4 * (sm_mhz or 1965.0) * 1e6                # warp instructions per second
+    return {'kernel': 'snp3_kernel', 'dp_cells_per_sec': snp_cells_per_s, 'fp64_fma_per_sec_measured': fma_rate,
+            'warp_instr_per_step': SNP_WARP_INSTR_PER_STEP, 'fp64_instr_per_step': SNP_FP64_INSTR_PER_STEP,
+            'cells_per_step': SNP_CELLS_PER_STEP,
+            'issue_frac': steps_per_s * SNP_WARP_INSTR_PER_STEP / issue_peak,
+            'fp64_pipe_frac': steps_per_s * SNP_FP64_INSTR_PER_STEP / fp64_peak if fp64_peak else None,
+            'source': 'SASS instruction counts x measured step rate; ncu counters of the same kernel in profiles/'}
 
 
 def ncu_traffic(reads_per_gpu):

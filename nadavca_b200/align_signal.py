@@ -92,6 +92,9 @@ def align_signal(reference_filename,
     (fast5 file names need h5py and are out of scope).  Reads without an alignment yield ``(read, None)`` as the
     reference's README promises.  All reads go through each stage as one GPU batch: refine -> linear
     renormalisation (round 0) -> refine (round 1) -> linear renormalisation (round 2)."""
+    if aligner is None:
+        raise ValueError('align_signal needs an `aligner` (any object with get_signal_alignment(read, bandwidth)): '
+                         'mapping reads with BWA is host work outside nadavca_b200')
     loaded = load_model_and_estimator(reference_filename, config, kmer_model, bwa_executable, aligner, reference)
     if loaded is None:
         return

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnadavca_b200.so")
-SOURCES = ["api.cu", "band.cu", "rows4.cu", "rows5.cu", "snp3.cu", "path2.cu", "finalize.cu", "select.cu", "microbench.cu"]
+SOURCES = ["api.cu", "band.cu", "rows4.cu", "rows5.cu", "snp3.cu", "path2.cu", "finalize.cu", "select.cu", "anchors.cu", "microbench.cu"]
 HEADERS = ["common.cuh", "dp3.cuh", "kernels.h", os.path.join("..", "..", "include", "nadavca_b200.h")]
 
 NVCC_FLAGS = [

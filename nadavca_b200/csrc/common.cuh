@@ -43,6 +43,23 @@ struct BatchDev {
   int32_t *max_width;  // per read
 };
 
+// Inputs of the batched anchor construction (anchors.cu), CSR over reads.
+struct AnchorBatch {
+  int n_reads;
+  const int32_t *cigar_len;   // operations of every read's CIGAR ...
+  const int8_t *cigar_op;     // ... 0 = M, 1 = I, 2 = D, 3 = S
+  const int64_t *cigar_off;
+  const int64_t *mapped_pos;  // 0-based position of the hit in the contig
+  const int32_t *reverse;
+  const int8_t *read_seq;     // basecalled bases 0..3 ...
+  const int32_t *mapping;     // ... and the sample index of each base (-1: not placed), Read.sequence_to_signal_mapping
+  const int64_t *read_off;
+  const int32_t *n_signal;    // len(read.normalized_signal)
+  const int8_t *genome;       // contig bases 0..3 (4 = other)
+  int64_t genome_len;
+  int bandwidth;
+};
+
 struct ReadView {
   int n, N, nb, na;
   const double *sig;

@@ -64,5 +64,8 @@ void nvbk_radix_hist(const double *d_values, int64_t n, int mode, double shift, 
 void nvbk_normalize_clip(const double *d_values, int64_t n, double shift, double scale, double lo, double hi,
                          double *d_out, cudaStream_t st);
 
+// anchors.cu: CIGAR -> matching-base anchors -> signal anchors and ranges (alignment.py:109-186), one warp per read
+void nvbk_anchors(const AnchorBatch &A, int32_t *d_anchors, int64_t *d_meta, cudaStream_t st);
+
 // microbench.cu
 float nvbk_fp64_fma_probe(int iters, int blocks, cudaStream_t st, double *d_sink);

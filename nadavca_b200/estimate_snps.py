@@ -21,8 +21,11 @@ def estimate_snps(reference_filename,
                   process_group=None):
     """Same arguments as the reference plus `aligner` (any object with get_signal_alignment(read, bandwidth);
     BWA mapping itself is out of scope) and `process_group` (consensus mode over several GPUs: every rank passes
-    its own shard of reads).  Returns a list of ``Chunk``: one per aligned read in input order when
-    `independent`, otherwise one per overlap group sorted by start."""
+    its own shard of reads).  Returns a list: with `independent` one entry per input read in input order (its
+    ``Chunk``, or None for a read without an alignment), otherwise one ``Chunk`` per overlap group sorted by start."""
+    if aligner is None:
+        raise ValueError('estimate_snps needs an `aligner` (any object with get_signal_alignment(read, bandwidth)): '
+                         'mapping reads with BWA is host work outside nadavca_b200')
     try:
         config = defaults.load_config(config)
     except FileNotFoundError:

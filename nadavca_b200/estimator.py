@@ -298,7 +298,8 @@ class ProbabilityEstimator:
 
     def estimate_probabilities(self, reference, reads, independent=False, process_group=None):
         """estimator.py:199-236.  `independent=True` treats every read as its own group (what estimate_snps does
-        with one call per read, estimate_snps.py:63-68) and returns one Chunk per aligned read in input order.
+        with one call per read, estimate_snps.py:63-68) and returns one entry per input read in input order: its
+        Chunk, or None when the read did not align / has no path.
         Otherwise chunks are summed per overlap group; with an initialised torch.distributed `process_group` the
         reads given to each rank are that rank's shard and the per-position sums are all-reduced over NCCL."""
         items, subs = self._run_estimate(reference, reads)
@@ -307,7 +308,7 @@ class ProbabilityEstimator:
                                          [tuple(it.apx.reference_range) for it in items], reference, independent,
                                          process_group)
             if stage is None:
-                return []
+                return [None] * len(reads) if independent else []
             groups, group_off, out, cov = stage
             probabilities = out.cpu().numpy()
             coverage = cov.cpu().numpy().astype(int)
@@ -316,8 +317,14 @@ class ProbabilityEstimator:
         finally:
             for batch, _ in subs:
                 batch.close()
-        return [Chunk(g[0], g[1], probabilities[group_off[i]:group_off[i + 1]].copy(),
-                      coverage[group_off[i]:group_off[i + 1]].copy()) for i, g in enumerate(groups)]
+        chunks = [Chunk(g[0], g[1], probabilities[group_off[i]:group_off[i + 1]].copy(),
+                        coverage[group_off[i]:group_off[i + 1]].copy()) for i, g in enumerate(groups)]
+        if not independent:
+            return chunks
+        # one entry per input read, in input order; None for reads that did not align or have no path (the reference
+        # indexes chunks[0] per read, estimate_snps.py:65-67, and crashes on those)
+        position = {id(it.read): i for i, it in enumerate(items)}
+        return [chunks[position[id(read)]] if id(read) in position else None for read in reads]
 
     def posterior_stage(self, batch, reverse, intervals, reference, independent=False, process_group=None,
                         plan=None, collective='auto', events=None):

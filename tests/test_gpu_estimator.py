@@ -130,7 +130,10 @@ def test_unaligned_reads_are_none(golden_estimator, default_model):
     res = est.get_refined_alignments([reads[0], stranger, reads[1]])
     assert res[1] is None and res[0] is not None and res[2] is not None
     chunks = est.estimate_probabilities(genome, [stranger], independent=True)
-    assert chunks == []
+    assert chunks == [None]
+    chunks = est.estimate_probabilities(genome, [reads[0], stranger, reads[1]], independent=True)
+    assert chunks[1] is None and chunks[0] is not None and chunks[2] is not None
+    assert est.estimate_probabilities(genome, [stranger], independent=False) == []
 
 
 def test_full_size_reads_properties_and_oracle(default_model):
