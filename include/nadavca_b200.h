@@ -174,6 +174,32 @@ int nvb_batch_chunk_values(nvb_batch *batch, const int32_t *reverse, double norm
  * for every read r with dest[r] >= 0 and status OK.  dest is a HOST array of n_reads row offsets. */
 int nvb_batch_scatter_add(nvb_batch *batch, const double *d_chunks, const int64_t *dest, double *d_acc,
                           int32_t *d_cov, void *stream);
+/* ---- batched anchor construction: replaces the per-read CIGAR walk and signal-alignment glue of
+ * ApproximateAligner (alignment.py:109-140 parse the CIGAR and keep matching bases; alignment.py:142-186 convert them
+ * to signal anchors and ranges).  Mapping the reads (BWA) stays on the host; its hits come in as CSR arrays. ---------- */
+typedef struct nvb_hits {
+  int32_t n_reads;
+  const int32_t *cigar_len;       /* CIGAR operations of all reads: lengths ... */
+  const int8_t *cigar_op;         /* ... and codes 0 = M, 1 = I, 2 = D, 3 = S */
+  const int64_t *cigar_off;       /* [n_reads + 1] */
+  const int64_t *mapped_position; /* 0-based position of the hit in the contig (SAM pos - 1) */
+  const int32_t *reverse;         /* 1 = the read maps to the reverse strand */
+  const int8_t *read_sequence;    /* basecalled bases 0..3 of all reads (Read.sequence) ... */
+  const int32_t *base_to_sample;  /* ... and the sample index of each base, -1 = not placed
+                                   * (Read.sequence_to_signal_mapping) */
+  const int64_t *read_off;        /* [n_reads + 1] */
+  const int32_t *n_signal;        /* len(Read.normalized_signal) per read */
+  const int8_t *d_genome;         /* DEVICE pointer: contig bases 0..3 (anything else: 4) */
+  int64_t genome_length;
+  int32_t bandwidth;
+} nvb_hits;
+/* anchors: host int32[2 * read_off[n_reads]]; the anchors of read b are the first meta[7b] (sample index - extended
+ * signal start, reference index - first anchored reference index) pairs from anchors + 2 * read_off[b].
+ * meta: host int64[7 * n_reads] = per read [n_anchors, reference_start, reference_end, signal_start, signal_end,
+ * read_sequence_start, read_sequence_end] in the conventions of ApproximateSignalAlignment (alignment.py:10-17,
+ * 153-186); n_anchors = 0 and -1s for a read without usable anchors. */
+int nvb_signal_anchors_batch(int device, const nvb_hits *hits, int32_t *anchors, int64_t *meta, void *stream);
+
 /* ---- pooled median / MAD normalisation on the device: replaces Read.normalize_reads (read.py:67-81) ------------
  * One pass of an exact most-significant-digit radix select over the order-preserving 64-bit keys of d_values (or of
  * |d_values - shift| when absolute_deviation != 0): ADDS to d_hist[256] the histogram of the 8 key bits below the

@@ -36,6 +36,17 @@ class NvbReads(ctypes.Structure):
     ]
 
 
+class NvbHits(ctypes.Structure):
+    _fields_ = [
+        ('n_reads', ctypes.c_int32),
+        ('cigar_len', c_i32p), ('cigar_op', c_i8p), ('cigar_off', c_i64p),
+        ('mapped_position', c_i64p), ('reverse', c_i32p),
+        ('read_sequence', c_i8p), ('base_to_sample', c_i32p), ('read_off', c_i64p),
+        ('n_signal', c_i32p),
+        ('d_genome', ctypes.c_void_p), ('genome_length', ctypes.c_int64), ('bandwidth', ctypes.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); every symbol declared in include/nadavca_b200.h
 SIGNATURES = {
     'nvb_abi_version': (ctypes.c_int, []),
@@ -81,6 +92,8 @@ SIGNATURES = {
                                               ctypes.c_void_p]),
     'nvb_batch_scatter_add': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_i64p, ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_void_p]),
+    'nvb_signal_anchors_batch': (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(NvbHits), c_i32p, c_i64p,
+                                                ctypes.c_void_p]),
     'nvb_radix_histogram_d': (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                                              ctypes.c_double, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p,
                                              ctypes.c_void_p]),

@@ -109,6 +109,104 @@ def signal_alignment_from_base_mapping(read, base_mapping, is_reverse_complement
                                       contig_name=contig_name)
 
 
+_CIGAR_CODES = {'M': 0, 'I': 1, 'D': 2, 'S': 3}
+
+
+def batch_signal_alignments(reads, hits, reference, bandwidth, device=0, contig_name='', d_reference=None):
+    """The anchor construction of ``ApproximateAligner.get_signal_alignment`` (alignment.py:109-186) for a whole
+    batch on the GPU (csrc/anchors.cu): `hits[i]` is the BWA hit of `reads[i]` as ``(cigar, mapped_position,
+    is_reverse_complement)`` -- the three fields the reference takes from the SAM record (alignment.py:100-107) -- or
+    None for an unmapped read.  Returns one ``ApproximateSignalAlignment`` (or None) per read, equal field by field
+    to ``signal_alignment_from_base_mapping(read, base_mapping_from_cigar(...), ...)``.  `d_reference`: the contig's
+    numeric codes already resident on the device (a torch int8 tensor) to skip its upload."""
+    import ctypes
+    import re
+    import torch
+    from . import _cabi
+    lib = _cabi.require_device()
+    idx = [i for i, h in enumerate(hits) if h is not None]
+    results = [None] * len(reads)
+    if not idx:
+        return results
+    dev = torch.device('cuda', int(device))
+    if d_reference is None:
+        d_reference = torch.as_tensor(reference_codes(reference), device=dev)
+    n = len(idx)
+    cig_len, cig_op, cig_off = [], [], numpy.zeros(n + 1, dtype=numpy.int64)
+    read_off = numpy.zeros(n + 1, dtype=numpy.int64)
+    seqs, maps = [], []
+    pos = numpy.zeros(n, dtype=numpy.int64)
+    rev = numpy.zeros(n, dtype=numpy.int32)
+    n_signal = numpy.zeros(n, dtype=numpy.int32)
+    for j, i in enumerate(idx):
+        cigar, mapped_position, is_rc = hits[i][:3]
+        ops = re.findall(r'(\d+)(.)', cigar)
+        for num, op in ops:
+            if op not in _CIGAR_CODES:
+                raise ValueError('Unknown cigar operation: {}'.format(op))
+            cig_len.append(int(num))
+            cig_op.append(_CIGAR_CODES[op])
+        cig_off[j + 1] = len(cig_len)
+        read = reads[i]
+        seq = reference_codes(read.sequence)
+        keys, samples = _mapping_arrays(read)
+        dense = numpy.full(len(seq), -1, dtype=numpy.int32)
+        ok = (keys >= 0) & (keys < len(seq))
+        dense[keys[ok]] = samples[ok]
+        seqs.append(seq)
+        maps.append(dense)
+        read_off[j + 1] = read_off[j] + len(seq)
+        pos[j], rev[j], n_signal[j] = mapped_position, int(bool(is_rc)), len(read.normalized_signal)
+    cig_len = numpy.ascontiguousarray(cig_len, dtype=numpy.int32)
+    cig_op = numpy.ascontiguousarray(cig_op, dtype=numpy.int8)
+    seq_all = numpy.ascontiguousarray(numpy.concatenate(seqs), dtype=numpy.int8)
+    map_all = numpy.ascontiguousarray(numpy.concatenate(maps), dtype=numpy.int32)
+    anchors = numpy.zeros(2 * int(read_off[-1]), dtype=numpy.int32)
+    meta = numpy.zeros(7 * n, dtype=numpy.int64)
+    h = _cabi.NvbHits(n, _cabi.ptr(cig_len, ctypes.c_int32), _cabi.ptr(cig_op, ctypes.c_int8),
+                      _cabi.ptr(cig_off, ctypes.c_int64), _cabi.ptr(pos, ctypes.c_int64), _cabi.ptr(rev, ctypes.c_int32),
+                      _cabi.ptr(seq_all, ctypes.c_int8), _cabi.ptr(map_all, ctypes.c_int32),
+                      _cabi.ptr(read_off, ctypes.c_int64), _cabi.ptr(n_signal, ctypes.c_int32),
+                      ctypes.c_void_p(d_reference.data_ptr()), len(reference), int(bandwidth))
+    stream = torch.cuda.current_stream(dev)
+    _cabi.check(lib.nvb_signal_anchors_batch(int(device), ctypes.byref(h), _cabi.ptr(anchors, ctypes.c_int32),
+                                             _cabi.ptr(meta, ctypes.c_int64), ctypes.c_void_p(stream.cuda_stream)),
+                'nvb_signal_anchors_batch')
+    meta = meta.reshape(n, 7)
+    for j, i in enumerate(idx):
+        count, ref_start, ref_end, sig_start, sig_end, read_start, read_end = (int(x) for x in meta[j])
+        if count == 0:
+            continue
+        is_rc = bool(rev[j])
+        part = reference[ref_start:ref_end]
+        if is_rc:
+            part = Genome.reverse_complement(part)
+        pairs = anchors[2 * read_off[j]:2 * read_off[j] + 2 * count].reshape(count, 2).astype(int)
+        results[i] = ApproximateSignalAlignment(alignment=pairs, signal_range=(sig_start, sig_end),
+                                                reference_range=(ref_start, ref_end),
+                                                read_sequence_range=(read_start, read_end), reverse_complement=is_rc,
+                                                reference_part=part,
+                                                contig_name=hits[i][3] if len(hits[i]) > 3 else contig_name)
+    return results
+
+
+_CODE_LUT = numpy.full(256, 4, dtype=numpy.int8)
+for _code, _base in enumerate('ACGT'):
+    _CODE_LUT[ord(_base)] = _code
+
+
+def reference_codes(sequence):
+    """Bases -> int8 codes 0..3 (4 for anything else); accepts a str, an array of 1-char strings or of codes."""
+    if isinstance(sequence, str):
+        return _CODE_LUT[numpy.frombuffer(sequence.encode('ascii'), dtype=numpy.uint8)]
+    arr = numpy.asarray(sequence)
+    if arr.dtype.kind in 'iu':
+        return arr.astype(numpy.int8)
+    if arr.size == 0:
+        return numpy.zeros(0, dtype=numpy.int8)
+    return _CODE_LUT[arr.astype('S1').view(numpy.uint8)]
+
+
 class ApproximateAligner:
     """Placeholder with the reference's constructor (alignment.py:19-40).  Mapping reads with BWA is host work that
     stays outside this package; plug in any aligner object exposing ``get_signal_alignment(read, bandwidth)``

@@ -949,6 +949,47 @@ int nvb_batch_scatter_add(nvb_batch *b, const double *d_chunks, const int64_t *d
   return NVB_OK;
 }
 
+int nvb_signal_anchors_batch(int device, const nvb_hits *h, int32_t *anchors, int64_t *meta, void *stream) {
+  if (!h || !anchors || !meta || h->n_reads < 0) return fail(NVB_EINVAL, "NULL argument");
+  if (nvb_device_count() <= device) return fail(NVB_ECUDA, "CUDA device %d not available (no CPU fallback)", device);
+  const int n = h->n_reads;
+  if (n == 0) return NVB_OK;
+  if (!h->cigar_len || !h->cigar_op || !h->cigar_off || !h->mapped_position || !h->reverse || !h->read_sequence ||
+      !h->base_to_sample || !h->read_off || !h->n_signal || !h->d_genome || h->bandwidth < 0)
+    return fail(NVB_EINVAL, "nvb_signal_anchors_batch: bad argument");
+  int rc;
+  if ((rc = check_offsets(h->cigar_off, n, "cigar"))) return rc;
+  if ((rc = check_offsets(h->read_off, n, "read"))) return rc;
+  CU(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n_ops = (size_t)h->cigar_off[n], n_bases = (size_t)h->read_off[n];
+  DevBuf<int32_t> d_len, d_rev, d_map, d_nsig, d_anchors;
+  DevBuf<int8_t> d_op, d_seq;
+  DevBuf<int64_t> d_coff, d_pos, d_roff, d_meta;
+  CU(upload(d_len, h->cigar_len, n_ops, st));
+  CU(upload(d_op, h->cigar_op, n_ops, st));
+  CU(upload(d_coff, h->cigar_off, (size_t)n + 1, st));
+  CU(upload(d_pos, h->mapped_position, (size_t)n, st));
+  CU(upload(d_rev, h->reverse, (size_t)n, st));
+  CU(upload(d_seq, h->read_sequence, n_bases, st));
+  CU(upload(d_map, h->base_to_sample, n_bases, st));
+  CU(upload(d_roff, h->read_off, (size_t)n + 1, st));
+  CU(upload(d_nsig, h->n_signal, (size_t)n, st));
+  CU(d_anchors.alloc(2 * n_bases));
+  CU(d_meta.alloc((size_t)7 * n));
+  AnchorBatch A;
+  A.n_reads = n;
+  A.cigar_len = d_len.p; A.cigar_op = d_op.p; A.cigar_off = d_coff.p; A.mapped_pos = d_pos.p; A.reverse = d_rev.p;
+  A.read_seq = d_seq.p; A.mapping = d_map.p; A.read_off = d_roff.p; A.n_signal = d_nsig.p;
+  A.genome = h->d_genome; A.genome_len = h->genome_length; A.bandwidth = h->bandwidth;
+  nvbk_anchors(A, d_anchors.p, d_meta.p, st);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(anchors, d_anchors.p, 2 * n_bases * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(meta, d_meta.p, (size_t)7 * n * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));  // the temporaries go back to the block cache on return
+  return NVB_OK;
+}
+
 int nvb_radix_histogram_d(int device, const double *d_values, int64_t n, int absolute_deviation, double shift,
                           uint64_t prefix, int fixed_bits, uint64_t *d_hist, void *stream) {
   if (!d_hist || n < 0 || (n > 0 && !d_values) || fixed_bits < 0 || fixed_bits > 56 || (fixed_bits & 7))

@@ -17,6 +17,7 @@ def declared_functions():
     text = open(HEADER).read()
     text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
     text = re.sub(r'typedef struct nvb_reads \{.*?\} nvb_reads;', '', text, flags=re.S)
+    text = re.sub(r'typedef struct nvb_hits \{.*?\} nvb_hits;', '', text, flags=re.S)
     names = re.findall(r'\b(nvb_[a-z0-9_]+)\s*\(', text)
     return sorted(set(names))
 

@@ -451,3 +451,63 @@ def test_device_normalisation_equals_numpy_bit_for_bit(lib_built, n_reads):
         assert b.normalized_signal.dtype == np.float64
         assert np.array_equal(a.normalized_signal, b.normalized_signal)
     assert max(abs(b.normalized_signal).max() for b in gpu) == 5.0
+
+
+def test_batched_anchor_construction_matches_host_glue(lib_built):
+    """csrc/anchors.cu (CIGAR walk -> matching-base anchors -> signal anchors and ranges) against the host functions
+    that restate alignment.py:109-186, field by field: both strands, insertions / deletions / soft clips, mismatches,
+    bases the basecaller did not place, a hit without any usable anchor and an unmapped read."""
+    from nadavca_b200 import alignment
+    from nadavca_b200.genome import Genome
+    from nadavca_b200.read import Read
+    rng = np.random.default_rng(301)
+    alpha = np.array(list('ACGT'))
+    G = 5000
+    genome = alpha[rng.integers(0, 4, size=G)]
+    reads, hits, want = [], [], []
+    for i in range(40):
+        is_rc = bool(i % 2)
+        start = int(rng.integers(0, G - 700))
+        ops, oriented, ref_pos = [], [], start
+        if rng.random() < 0.5:
+            n = int(rng.integers(1, 20)); ops.append((n, 'S')); oriented.extend(alpha[rng.integers(0, 4, size=n)])
+        for _ in range(int(rng.integers(3, 40))):
+            n = int(rng.integers(1, 45))
+            seg = genome[ref_pos:ref_pos + n].copy()
+            flip = rng.random(n) < 0.08
+            seg[flip] = alpha[rng.integers(0, 4, size=int(flip.sum()))]
+            ops.append((n, 'M')); oriented.extend(seg); ref_pos += n
+            kind = rng.random()
+            if kind < 0.3:
+                n = int(rng.integers(1, 6)); ops.append((n, 'I')); oriented.extend(alpha[rng.integers(0, 4, size=n)])
+            elif kind < 0.6:
+                n = int(rng.integers(1, 6)); ops.append((n, 'D')); ref_pos += n
+        if rng.random() < 0.5:
+            n = int(rng.integers(1, 20)); ops.append((n, 'S')); oriented.extend(alpha[rng.integers(0, 4, size=n)])
+        oriented = np.array(oriented)
+        sequence = Genome.reverse_complement(oriented) if is_rc else oriented
+        L = len(sequence)
+        samples = np.cumsum(rng.integers(2, 15, size=L)) + 100
+        placed = rng.random(L) < (0.0 if i == 7 else 0.9)   # read 7: no base was placed in the signal
+        read = Read.from_arrays(rng.normal(90, 15, size=int(samples[-1]) + 150), sequence,
+                                {int(b): int(samples[b]) for b in range(L) if placed[b]})
+        Read.normalize_reads([read])
+        cigar = ''.join('%d%s' % op for op in ops)
+        reads.append(read)
+        hits.append(None if i == 11 else (cigar, start, is_rc))
+        if i == 11:
+            want.append(None)
+            continue
+        mapping = alignment.base_mapping_from_cigar(cigar, start, sequence, genome, is_rc)
+        want.append(alignment.signal_alignment_from_base_mapping(read, mapping, is_rc, 'contig', genome, 37))
+    got = alignment.batch_signal_alignments(reads, hits, genome, 37, contig_name='contig')
+    assert want[7] is None and want[11] is None and sum(w is not None for w in want) >= 36
+    for g, w in zip(got, want):
+        if w is None:
+            assert g is None
+            continue
+        assert np.array_equal(g.alignment, w.alignment)
+        assert g.signal_range == tuple(w.signal_range) and g.reference_range == tuple(w.reference_range)
+        assert g.read_sequence_range == tuple(w.read_sequence_range)
+        assert g.reverse_complement == w.reverse_complement and g.contig_name == w.contig_name
+        assert np.array_equal(g.reference_part, w.reference_part)
