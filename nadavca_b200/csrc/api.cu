@@ -201,6 +201,7 @@ struct nvb_batch {
   DevBuf<int64_t> d_mat_base, d_dp_base, d_rec_base;
   int64_t ws_limit = 0;
   int64_t launches = 0;
+  int path_pk = 11;  // columns per lane of the path search (path2.cu), from the widest band row of the batch
   // Streams this batch has work on.  Results are read back on `run_stream` (the stream of the latest run); destroying
   // the batch drains every stream that may still be using its buffers -- never the whole device.
   cudaStream_t run_stream = nullptr;
@@ -407,6 +408,10 @@ int batch_init(nvb_batch *b, const nvb_reads *r) {
     b->flags[i] = ((summary[4 * i + 3] >> 32) & 1) ? NVB_READ_BAD_BAND : 0;
     b->no_rotation[i] = (int32_t)((summary[4 * i + 3] >> 33) & 1);
   }
+  int widest = 0;
+  for (int i = 0; i < n; i++)
+    if (!b->flags[i]) widest = std::max(widest, (int)b->maxw[i]);
+  b->path_pk = nvbk_path2_columns_per_lane(widest);
   return NVB_OK;
 }
 
@@ -445,7 +450,7 @@ int64_t record_words(const nvb_batch *b, int i, int mode) {
   if (b->flags[i]) return 0;
   const int64_t n = b->ref_off[i + 1] - b->ref_off[i];
   const int64_t rows = (mode == NVB_MODE_TRANS) ? 2 * n : n + 1;
-  const int chunk = nvbk_path2_chunk_columns();
+  const int chunk = 32 * b->path_pk;
   const int64_t nch = (b->maxw[i] + chunk - 1) / chunk;
   return rows * nch * 32;
 }
@@ -604,7 +609,7 @@ int nvb_batch_refine(nvb_batch *b, int model_transitions, void *stream) {
     if (!g_opt.skip_path) {  // debugging aid: keep the prefix plane for nvb_batch_debug_rows
       StageTimer t(b, 1, st);
       nvbk_score(w.cells, ws.pF.p, ws.pX.p, ws.sF.p, ws.sX.p, st);
-      if (nvbk_path2(b->dev, mode, w.b0, w.b1, b->d_mat_base.p, ws.pF.p, ws.records.p, b->d_rec_base.p,
+      if (nvbk_path2(b->dev, mode, w.b0, w.b1, b->path_pk, b->d_mat_base.p, ws.pF.p, ws.records.p, b->d_rec_base.p,
                      ws.dp.p, b->d_dp_base.p, w.maxw, b->d_events.p, b->d_status.p, st))
         return fail(NVB_ECUDA, "path kernel: cannot reserve shared memory");
     }

@@ -158,7 +158,7 @@ struct RingState {
 };
 // NS slots of 32 samples, NS mbarriers, the state: NS = 8 for the rotating sweep (window of up to 64 samples), 4 for the
 // striped sweep (window of 32)
-constexpr int ring_bytes(int NS) { return NS * 256 + NS * 8 + (int)sizeof(RingState); }
+__host__ __device__ constexpr int ring_bytes(int NS) { return NS * 256 + NS * 8 + (int)sizeof(RingState); }
 
 template <int NS>
 struct SignalRing {

@@ -30,10 +30,10 @@ int nvbk_snp2(const ModelDev &M, const BatchDev &B, int wobbling, int b0, int b1
 
 // path2.cu: posterior scores (in place over the prefix mantissa plane), max-product path with one record bit per
 // cell, traceback (dtw.cpp:199-227).  nvbk_path2 returns -1 when the shared-memory reservation fails.
-int nvbk_path2_chunk_columns();
+int nvbk_path2_columns_per_lane(int maxw);
 void nvbk_score(int64_t total_cells, double *pF, const int32_t *pX, const double *sF, const int32_t *sX,
                 cudaStream_t st);
-int nvbk_path2(const BatchDev &B, int mode, int b0, int b1, const int64_t *d_mat_base, const double *score,
+int nvbk_path2(const BatchDev &B, int mode, int b0, int b1, int pk, const int64_t *d_mat_base, const double *score,
                uint32_t *d_records, const int64_t *d_rec_base, double *d_dp, const int64_t *d_dp_base, int wave_maxw,
                int32_t *d_events, int32_t *d_status, cudaStream_t st);
 

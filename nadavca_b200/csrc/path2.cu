@@ -19,9 +19,6 @@
 
 namespace {
 
-constexpr int PK = 11;               // columns per lane and chunk; odd => conflict-free shared-memory strides
-constexpr int PCHUNK = PK * NVB_WARP;  // 352 columns per chunk
-
 __global__ void __launch_bounds__(256) score_kernel(int64_t total, double *pF, const int32_t *pX, const double *sF,
                                                     const int32_t *sX) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -47,12 +44,15 @@ __device__ __forceinline__ double warp_excl_max(double x, int lane) {
   return lane ? y : nvb_neg_inf();
 }
 
-// Last record bit at relative index <= t of a row whose record words start at `fl` (nch chunks of 32 words).
-// `w0` is the already loaded word of this lane for chunk t / PCHUNK when have_w0.  Returns -1 when there is none.
+// Last record bit at relative index <= t of a row whose record words start at `fl` (chunks of 32 words, PK columns
+// per word).  `w0` is the already loaded word of this lane for chunk t / (32 PK) when have_w0.  Returns -1 when there
+// is none.  Called by one whole warp.
+template <int PK>
 __device__ __forceinline__ int find_last_record(const uint32_t *fl, int t, int lane, bool have_w0, uint32_t w0) {
+  constexpr int PCH = PK * NVB_WARP;
   if (t < 0) return -1;
-  int ch = t / PCHUNK;
-  int tl = t - ch * PCHUNK;
+  int ch = t / PCH;
+  int tl = t - ch * PCH;
   for (;;) {
     uint32_t w = have_w0 ? w0 : __ldcg(fl + ch * NVB_WARP + lane);
     have_w0 = false;
@@ -63,38 +63,47 @@ __device__ __forceinline__ int find_last_record(const uint32_t *fl, int t, int l
     if (any) {
       const int hl = 31 - __clz(any);
       const uint32_t wv = __shfl_sync(NVB_FULL, w, hl);
-      return ch * PCHUNK + hl * PK + (31 - __clz(wv));
+      return ch * PCH + hl * PK + (31 - __clz(wv));
     }
     if (--ch < 0) return -1;
-    tl = PCHUNK - 1;
+    tl = PCH - 1;
   }
 }
 
-__global__ void __launch_bounds__(128) path2_kernel(BatchDev B, int mode, int b0, int n_items, const int64_t *mat_base,
+// One CTA per read, NWP = blockDim.x / 32 warps.  A row is cut into chunks of 32 * PK consecutive columns (PK per
+// lane); chunk ch of a row is worked by warp ch % NWP, all chunks of a round of NWP at the same time: each warp scans
+// its chunk, publishes the chunk maximum, and after a CTA barrier takes the maximum of the chunks in front of it as
+// its carry.  Rows are inherently sequential (dp[r] needs the prefix maxima of dp[r-1]); what the extra warps buy is a
+// row in ~1/NWP of the instructions per warp -- the kernel is bound by the dependent-issue latency of one warp
+// (ncu, profiles/r01e: 870 warp instructions per 301-column row at PK = 11, 3.3 us per row).
+template <int PK>
+__global__ void __launch_bounds__(256) path2_kernel(BatchDev B, int mode, int b0, int n_items, const int64_t *mat_base,
                                                     const double *score, uint32_t *records, const int64_t *rec_base,
                                                     double *gscratch, const int64_t *dp_base, int smem_width,
                                                     int32_t *events, int32_t *status) {
   extern __shared__ double smem[];
-  const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item = blockIdx.x * (blockDim.x >> 5) + wic;
+  constexpr int PCH = PK * NVB_WARP;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NWP = blockDim.x >> 5;
+  const int item = blockIdx.x;
   if (item >= n_items) return;
   const int b = b0 + item;
   ReadView v = read_view(B, b);
   const int n = v.n;
   int32_t *ev = events + 2 * B.ref_off[b];
   if (B.flags[b]) {
-    for (int i = lane; i < 2 * n; i += NVB_WARP) ev[i] = -1;
-    if (lane == 0) status[b] = B.flags[b];
+    for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) ev[i] = -1;
+    if (threadIdx.x == 0) status[b] = B.flags[b];
     return;
   }
   const double NINF = nvb_neg_inf();
   const int R = (mode == NVB_MODE_TRANS) ? 2 * n : n + 1;
   const int maxw = B.max_width[b];
-  const int nch = (maxw + PCHUNK - 1) / PCHUNK;
+  const int nch = (maxw + PCH - 1) / PCH;
   const double *SC = score + mat_base[b];
   uint32_t *FL = records + rec_base[b];
+  double *tot = smem;  // [2][8]: chunk maxima of the current round, double buffered over rounds
   double *Mprev, *Mcur;
-  if (smem_width > 0) { Mprev = smem + (size_t)wic * 2 * smem_width; Mcur = Mprev + smem_width; }
+  if (smem_width > 0) { Mprev = smem + 16; Mcur = Mprev + smem_width; }
   else { Mprev = gscratch + dp_base[b]; Mcur = Mprev + maxw; }
 
   int s, e, ps = 0, pe = -1;
@@ -102,30 +111,32 @@ __global__ void __launch_bounds__(128) path2_kernel(BatchDev B, int mode, int b0
   row_geom2(v, mode, 0, s, e, off);
   double cur[PK], nxt[PK];
   {
-    const int c0 = s + lane * PK;
+    const int c0 = s + warp * PCH + lane * PK;
 #pragma unroll
     for (int j = 0; j < PK; j++) cur[j] = (c0 + j <= e) ? __ldg(SC + off + (c0 + j - s)) : NINF;
   }
+  int flip = 0;
   for (int r = 0; r < R; r++) {
     const int m = (r == 0) ? 0 : ((mode == NVB_MODE_TRANS && ((r - 1) & 1)) ? 0 : B.mel);  // dtw.cpp:165-179
-    // prefetch the first chunk of the next row while this one is processed
+    // prefetch this warp's first chunk of the next row while this one is processed
     int ns = 0, ne = -1;
     int64_t noff = 0;
     if (r + 1 < R) {
       row_geom2(v, mode, r + 1, ns, ne, noff);
-      const int c0 = ns + lane * PK;
+      const int c0 = ns + warp * PCH + lane * PK;
 #pragma unroll
       for (int j = 0; j < PK; j++) nxt[j] = (c0 + j <= ne) ? __ldg(SC + noff + (c0 + j - ns)) : NINF;
     }
     const int w = e - s + 1;
-    double chunk_carry = NINF;
-    for (int ch = 0; ch * PCHUNK < w; ch++) {
-      const int c0 = s + ch * PCHUNK + lane * PK;
+    double round_carry = NINF;  // maximum over all chunks of the rounds before this one
+    for (int base = 0; base * PCH < w; base += NWP) {
+      const int ch = base + warp;
+      const int c0 = s + ch * PCH + lane * PK;
       double dp[PK];
 #pragma unroll
       for (int j = 0; j < PK; j++) {
         const int c = c0 + j;
-        double sc = (ch == 0) ? cur[j] : ((c <= e) ? __ldg(SC + off + (c - s)) : NINF);
+        double sc = (base == 0) ? cur[j] : ((c <= e) ? __ldg(SC + off + (c - s)) : NINF);
         if (r > 0) {
           // best predecessor over i' <= c - m inside the previous row's band (node.cpp:68-89)
           const int q = c - m;
@@ -134,27 +145,38 @@ __global__ void __launch_bounds__(128) path2_kernel(BatchDev B, int mode, int b0
         }
         dp[j] = (c <= e) ? sc : NINF;
       }
-      // lane-local inclusive prefix maxima, then the warp-wide exclusive carry
-      double lm[PK];
-      lm[0] = dp[0];
+      // lane-local inclusive prefix maxima, the warp-wide exclusive carry, then the carry over the chunks in front
+      double lm = dp[0];
 #pragma unroll
-      for (int j = 1; j < PK; j++) lm[j] = fmax(lm[j - 1], dp[j]);
-      const double carry = fmax(chunk_carry, warp_excl_max(lm[PK - 1], lane));
+      for (int j = 1; j < PK; j++) lm = fmax(lm, dp[j]);
+      const double lane_excl = warp_excl_max(lm, lane);
+      double *T = tot + 8 * flip;
+      if (NWP > 1) {
+        const double chunk_max = __shfl_sync(NVB_FULL, fmax(lane_excl, lm), NVB_WARP - 1);
+        if (lane == 0) T[warp] = chunk_max;
+        __syncthreads();
+      }
+      double carry = round_carry;
+      if (NWP > 1) {
+        for (int k = 0; k < warp; k++) carry = fmax(carry, T[k]);
+      }
       uint32_t bits = 0;
-      double before = carry;
+      double before = fmax(carry, lane_excl);
 #pragma unroll
       for (int j = 0; j < PK; j++) {
         if (dp[j] > before) bits |= 1u << j;  // strict '>': the lowest index wins ties (node.cpp:72-75)
         before = fmax(before, dp[j]);
         if (c0 + j <= e) Mcur[c0 + j - s] = before;
       }
-      FL[((int64_t)r * nch + ch) * NVB_WARP + lane] = bits;
-      chunk_carry = __shfl_sync(NVB_FULL, before, NVB_WARP - 1);
+      if (ch < nch) FL[((int64_t)r * nch + ch) * NVB_WARP + lane] = bits;
+      if (NWP > 1) {
+        for (int k = 0; k < NWP; k++) round_carry = fmax(round_carry, T[k]);
+        flip ^= 1;
+      } else {
+        round_carry = __shfl_sync(NVB_FULL, before, NVB_WARP - 1);
+      }
     }
-    __syncwarp();
-#ifdef NVB_TRACE
-    if (lane == 0 && b == b0) printf("row %d band %d..%d off %lld m %d carry %g cur0 %g\n", r, s, e, (long long)off, m, chunk_carry, cur[0]);
-#endif
+    __syncthreads();  // Mcur is complete: the next row reads it as Mprev (one warp per read: a warp barrier would do)
     double *t = Mprev; Mprev = Mcur; Mcur = t;
     ps = s; pe = e;
     s = ns; e = ne; off = noff;
@@ -162,12 +184,13 @@ __global__ void __launch_bounds__(128) path2_kernel(BatchDev B, int mode, int b0
     for (int j = 0; j < PK; j++) cur[j] = nxt[j];
   }
   __threadfence_block();
-  __syncwarp();
+  __syncthreads();
+  if (warp != 0) return;
 
   // GetBestIndex on the last row (node.cpp:48-58): first index of the row maximum = its last record
   int rs, re;
   row_geom2(v, mode, R - 1, rs, re, off);
-  int rel = find_last_record(FL + (int64_t)(R - 1) * nch * NVB_WARP, re - rs, lane, false, 0);
+  int rel = find_last_record<PK>(FL + (int64_t)(R - 1) * nch * NVB_WARP, re - rs, lane, false, 0);
   if (rel < 0) {  // no valid path in the band (dtw.cpp:211-213)
     for (int i = lane; i < 2 * n; i += NVB_WARP) ev[i] = -1;
     if (lane == 0) status[b] = 1;
@@ -202,16 +225,39 @@ __global__ void __launch_bounds__(128) path2_kernel(BatchDev B, int mode, int b0
         int64_t qoff;
         row_geom2(v, mode, r - 1, qs, qe, qoff);
         const int q = min(col - m, qe) - qs;
-        rel = find_last_record(FL + (int64_t)(r - 1) * nch * NVB_WARP, q, lane, nch == 1, pre[g]);
+        rel = find_last_record<PK>(FL + (int64_t)(r - 1) * nch * NVB_WARP, q, lane, nch == 1, pre[g]);
       }
     }
   }
   if (lane == 0) status[b] = 0;
 }
 
+template <int PK>
+int launch_path(const BatchDev &B, int mode, int b0, int n_items, const int64_t *d_mat_base, const double *score,
+                uint32_t *d_records, const int64_t *d_rec_base, double *d_dp, const int64_t *d_dp_base, int wave_maxw,
+                int32_t *d_events, int32_t *d_status, cudaStream_t st) {
+  // warps per read: one per chunk of the widest row, at most 8 (wider rows take several rounds)
+  int warps = (wave_maxw + PK * NVB_WARP - 1) / (PK * NVB_WARP);
+  warps = warps < 1 ? 1 : (warps > 8 ? 8 : warps);
+  // shared memory: the chunk maxima and two prefix-maximum rows; global scratch rows for very wide bands
+  int smem_width = wave_maxw;
+  size_t smem = 16 * sizeof(double) + (size_t)2 * wave_maxw * sizeof(double);
+  if (smem > 200 * 1024) { smem_width = 0; smem = 16 * sizeof(double); }
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(path2_kernel<PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -1;
+  }
+  path2_kernel<PK><<<n_items, warps * NVB_WARP, smem, st>>>(B, mode, b0, n_items, d_mat_base, score, d_records,
+                                                             d_rec_base, d_dp, d_dp_base, smem_width, d_events,
+                                                             d_status);
+  return 0;
+}
+
 }  // namespace
 
-int nvbk_path2_chunk_columns() { return PCHUNK; }
+// Columns per lane of the path search for a batch whose widest band row has `maxw` columns: 4 warps cover rows of
+// up to 384 columns at 3 per lane, 768 at 6; wider rows use 11 per lane and up to 8 warps.
+int nvbk_path2_columns_per_lane(int maxw) { return maxw <= 384 ? 3 : (maxw <= 768 ? 6 : 11); }
 
 void nvbk_score(int64_t total_cells, double *pF, const int32_t *pX, const double *sF, const int32_t *sX,
                 cudaStream_t st) {
@@ -221,22 +267,16 @@ void nvbk_score(int64_t total_cells, double *pF, const int32_t *pX, const double
   score_kernel<<<blocks, 256, 0, st>>>(total_cells, pF, pX, sF, sX);
 }
 
-int nvbk_path2(const BatchDev &B, int mode, int b0, int b1, const int64_t *d_mat_base, const double *score,
+// pk: columns per lane the record words of this batch were laid out for (nvbk_path2_columns_per_lane of the batch's
+// widest row).  Returns -1 when the shared-memory reservation fails.
+int nvbk_path2(const BatchDev &B, int mode, int b0, int b1, int pk, const int64_t *d_mat_base, const double *score,
                uint32_t *d_records, const int64_t *d_rec_base, double *d_dp, const int64_t *d_dp_base, int wave_maxw,
                int32_t *d_events, int32_t *d_status, cudaStream_t st) {
   const int n_items = b1 - b0;
   if (n_items <= 0) return 0;
-  // shared memory: two prefix-maximum rows per warp; fall back to the global scratch rows for very wide bands
-  const size_t per_warp = (size_t)2 * wave_maxw * sizeof(double);
-  int warps = 4, smem_width = wave_maxw;
-  while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
-  if (per_warp * warps > 200 * 1024) smem_width = 0;
-  const size_t smem = smem_width ? per_warp * warps : 0;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(path2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return -1;
+  switch (pk) {
+    case 3: return launch_path<3>(B, mode, b0, n_items, d_mat_base, score, d_records, d_rec_base, d_dp, d_dp_base, wave_maxw, d_events, d_status, st);
+    case 6: return launch_path<6>(B, mode, b0, n_items, d_mat_base, score, d_records, d_rec_base, d_dp, d_dp_base, wave_maxw, d_events, d_status, st);
+    default: return launch_path<11>(B, mode, b0, n_items, d_mat_base, score, d_records, d_rec_base, d_dp, d_dp_base, wave_maxw, d_events, d_status, st);
   }
-  path2_kernel<<<(n_items + warps - 1) / warps, warps * NVB_WARP, smem, st>>>(
-      B, mode, b0, n_items, d_mat_base, score, d_records, d_rec_base, d_dp, d_dp_base, smem_width, d_events, d_status);
-  return 0;
 }

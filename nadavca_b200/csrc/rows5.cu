@@ -23,8 +23,14 @@ namespace {
 #define NVB_ROT_MIN_BLOCKS 8  // 64-thread CTAs per SM: 128 registers per thread, 16 warps per SM
 #endif
 
-constexpr int TS = 4;       // steps per store tile; pairs are (de)activated only at multiples of TS
-constexpr int TSTRIDE = 5;  // padded tile row stride
+#ifndef NVB_ROT_TS
+#define NVB_ROT_TS 8
+#endif
+// Steps per store tile; pairs are (de)activated only at multiples of TS.  The per-tile work (slot management, ring
+// upkeep, the transposing flush: ~300 warp instructions) is amortised over TS steps; 8 is the largest value the
+// slot-reuse guarantee of band.cu (be[j] - bs[j+63] <= 48) allows.
+constexpr int TS = NVB_ROT_TS;
+constexpr int TSTRIDE = TS + 1;  // padded tile row stride
 
 struct RowMeta {
   long long off;  // offset of the row's first cell in the matrix planes
@@ -38,7 +44,11 @@ struct StoreTile {
   RowMeta *meta;  // [32]
 };
 constexpr size_t kTileBytes = 32 * TSTRIDE * (sizeof(double) + sizeof(int32_t)) + 32 * sizeof(RowMeta);
-constexpr size_t kWarpBytes = ((4 * kTileBytes + ring_bytes(8) + 255) / 256) * 256;  // keeps every ring 256-byte aligned
+// tiles per warp: the B rows of the two slots, plus their A rows in the transition sweep (the only one that stores them)
+__host__ __device__ constexpr int tiles_per_warp(int mode) { return mode == NVB_MODE_TRANS ? 4 : 2; }
+__host__ __device__ constexpr size_t warp_bytes(int mode) {  // keeps every ring 256-byte aligned
+  return ((tiles_per_warp(mode) * kTileBytes + ring_bytes(8) + 255) / 256) * 256;
+}
 
 template <bool REV>
 __device__ __forceinline__ void flush_tile(const StoreTile &tile, double *F, int32_t *X, int C0, int t0, int lane) {
@@ -198,7 +208,8 @@ __device__ void sweep_rotate(const ModelDev &M, const ReadView &v, double *F, in
                              const StoreTile (&tiles)[4], const SignalRing<8> &R) {
   const int n = v.n;
   constexpr bool TRANS = (MODE == NVB_MODE_TRANS);
-  const StoreTile &tPB = tiles[0], &tPA = tiles[1], &tSB = tiles[2], &tSA = tiles[3];
+  // tiles: B rows of slot P and slot Q2, then (transition sweep only) their A rows
+  const StoreTile &tPB = tiles[0], &tSB = tiles[1], &tPA = tiles[TRANS ? 2 : 0], &tSA = tiles[TRANS ? 3 : 1];
 
   // all-ones first row (dtw.cpp:50,66,182,190): written to HBM here, generated on the fly for pair 0
   const int j0 = REV ? n : 0;
@@ -306,10 +317,10 @@ __global__ void __launch_bounds__(64, NVB_ROT_MIN_BLOCKS) sweep5_kernel(ModelDev
   if (item >= n_items) return;
   const int b = b0 + (item >> 1);
   if (B.flags[b] != 0) return;  // bad band
-  unsigned char *base = reinterpret_cast<unsigned char *>(smem_raw) + (size_t)warp * kWarpBytes;
+  unsigned char *base = reinterpret_cast<unsigned char *>(smem_raw) + (size_t)warp * warp_bytes(MODE);
   StoreTile tiles[4];
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
+  for (int i = 0; i < tiles_per_warp(MODE); i++) {
     unsigned char *p = base + (size_t)i * kTileBytes;
     tiles[i].f = reinterpret_cast<double *>(p);
     tiles[i].meta = reinterpret_cast<RowMeta *>(tiles[i].f + 32 * TSTRIDE);
@@ -319,7 +330,7 @@ __global__ void __launch_bounds__(64, NVB_ROT_MIN_BLOCKS) sweep5_kernel(ModelDev
   const int64_t mb = mat_base[b];
   // signal ring (dp3.cuh) behind the four store tiles: 8 chunks of 32 samples + 8 mbarriers, filled by TMA bulk copies
   SignalRing<8> R;
-  ring_init(R, base + 4 * kTileBytes, B.signal, B.sig_off[b], B.sig_off[B.n_reads], lane);
+  ring_init(R, base + tiles_per_warp(MODE) * kTileBytes, B.signal, B.sig_off[b], B.sig_off[B.n_reads], lane);
   if (item & 1) sweep_rotate<MEL, MODE, true>(M, v, sF + mb, sX + mb, lane, tiles, R);
   else sweep_rotate<MEL, MODE, false>(M, v, pF + mb, pX + mb, lane, tiles, R);
 }
@@ -327,8 +338,8 @@ __global__ void __launch_bounds__(64, NVB_ROT_MIN_BLOCKS) sweep5_kernel(ModelDev
 template <int MEL, int MODE>
 void launch_mode(const ModelDev &M, const BatchDev &B, int b0, int n_items, const int64_t *mb, double *pF, int32_t *pX,
                  double *sF, int32_t *sX, cudaStream_t st) {
-  const int warps = 2;  // 2 x (4 tiles x 2.7 KB + 2 KB ring) = 26 KB per CTA
-  const size_t smem = (size_t)warps * kWarpBytes;
+  const int warps = 2;  // 2 x (2 tiles x 4.2 KB + 2 KB ring) = 21 KB per CTA (38 KB in the transition sweep)
+  const size_t smem = (size_t)warps * warp_bytes(MODE);
   sweep5_kernel<MEL, MODE><<<(n_items + warps - 1) / warps, warps * NVB_WARP, smem, st>>>(M, B, b0, n_items, mb, pF, pX,
                                                                                          sF, sX);
 }
