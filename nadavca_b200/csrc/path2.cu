@@ -80,7 +80,7 @@ template <int PK>
 __global__ void __launch_bounds__(256) path2_kernel(BatchDev B, int mode, int b0, int n_items, const int64_t *mat_base,
                                                     const double *score, uint32_t *records, const int64_t *rec_base,
                                                     double *gscratch, const int64_t *dp_base, int smem_width,
-                                                    int32_t *events, int32_t *status) {
+                                                    int stage_words, int32_t *events, int32_t *status) {
   extern __shared__ double smem[];
   constexpr int PCH = PK * NVB_WARP;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NWP = blockDim.x >> 5;
@@ -106,27 +106,37 @@ __global__ void __launch_bounds__(256) path2_kernel(BatchDev B, int mode, int b0
   if (smem_width > 0) { Mprev = smem + 16; Mcur = Mprev + smem_width; }
   else { Mprev = gscratch + dp_base[b]; Mcur = Mprev + maxw; }
 
-  int s, e, ps = 0, pe = -1;
-  int64_t off;
-  row_geom2(v, mode, 0, s, e, off);
-  double cur[PK], nxt[PK];
-  {
-    const int c0 = s + warp * PCH + lane * PK;
+  // Rows in flight: geometry and this warp's first-chunk scores of rows r .. r+D-1 are requested D rows ahead (one row
+  // of work is shorter than a global-load round trip: with a single row of look-ahead 21 % of the stall samples were
+  // the first use of the prefetched scores, ncu profiles/r02f).  Slot 0 is the current row.
+  constexpr int D = PK <= 3 ? 4 : (PK <= 6 ? 2 : 1);
+  int qs[D + 1], qe[D + 1];
+  double qsc[D + 1][PK];
+  auto fetch = [&](int slot, int r) {
+    qs[slot] = 0; qe[slot] = -1;
+    if (r < R) {
+      int64_t o;
+      row_geom2(v, mode, r, qs[slot], qe[slot], o);
+      const int c0 = qs[slot] + warp * PCH + lane * PK;
 #pragma unroll
-    for (int j = 0; j < PK; j++) cur[j] = (c0 + j <= e) ? __ldg(SC + off + (c0 + j - s)) : NINF;
-  }
+      for (int j = 0; j < PK; j++)
+        qsc[slot][j] = (c0 + j <= qe[slot]) ? __ldg(SC + o + (c0 + j - qs[slot])) : NINF;
+    } else {
+#pragma unroll
+      for (int j = 0; j < PK; j++) qsc[slot][j] = NINF;
+    }
+  };
+#pragma unroll
+  for (int d = 0; d < D; d++) fetch(d, d);
+  int ps = 0, pe = -1;
   int flip = 0;
   for (int r = 0; r < R; r++) {
     const int m = (r == 0) ? 0 : ((mode == NVB_MODE_TRANS && ((r - 1) & 1)) ? 0 : B.mel);  // dtw.cpp:165-179
-    // prefetch this warp's first chunk of the next row while this one is processed
-    int ns = 0, ne = -1;
-    int64_t noff = 0;
-    if (r + 1 < R) {
-      row_geom2(v, mode, r + 1, ns, ne, noff);
-      const int c0 = ns + warp * PCH + lane * PK;
+    fetch(D, r + D);
+    const int s = qs[0], e = qe[0];
+    double cur[PK];
 #pragma unroll
-      for (int j = 0; j < PK; j++) nxt[j] = (c0 + j <= ne) ? __ldg(SC + noff + (c0 + j - ns)) : NINF;
-    }
+    for (int j = 0; j < PK; j++) cur[j] = qsc[0][j];
     const int w = e - s + 1;
     double round_carry = NINF;  // maximum over all chunks of the rounds before this one
     for (int base = 0; base * PCH < w; base += NWP) {
@@ -136,7 +146,13 @@ __global__ void __launch_bounds__(256) path2_kernel(BatchDev B, int mode, int b0
 #pragma unroll
       for (int j = 0; j < PK; j++) {
         const int c = c0 + j;
-        double sc = (base == 0) ? cur[j] : ((c <= e) ? __ldg(SC + off + (c - s)) : NINF);
+        double sc = cur[j];
+        if (base > 0) {  // rows wider than NWP chunks: later rounds load their scores directly
+          int ts, te;
+          int64_t off;
+          row_geom2(v, mode, r, ts, te, off);
+          sc = (c <= e) ? __ldg(SC + off + (c - s)) : NINF;
+        }
         if (r > 0) {
           // best predecessor over i' <= c - m inside the previous row's band (node.cpp:68-89)
           const int q = c - m;
@@ -179,57 +195,81 @@ __global__ void __launch_bounds__(256) path2_kernel(BatchDev B, int mode, int b0
     __syncthreads();  // Mcur is complete: the next row reads it as Mprev (one warp per read: a warp barrier would do)
     double *t = Mprev; Mprev = Mcur; Mcur = t;
     ps = s; pe = e;
-    s = ns; e = ne; off = noff;
 #pragma unroll
-    for (int j = 0; j < PK; j++) cur[j] = nxt[j];
+    for (int d = 0; d < D; d++) {
+      qs[d] = qs[d + 1]; qe[d] = qe[d + 1];
+#pragma unroll
+      for (int j = 0; j < PK; j++) qsc[d][j] = qsc[d + 1][j];
+    }
   }
   __threadfence_block();
   __syncthreads();
-  if (warp != 0) return;
 
-  // GetBestIndex on the last row (node.cpp:48-58): first index of the row maximum = its last record
-  int rs, re;
-  row_geom2(v, mode, R - 1, rs, re, off);
-  int rel = find_last_record<PK>(FL + (int64_t)(R - 1) * nch * NVB_WARP, re - rs, lane, false, 0);
-  if (rel < 0) {  // no valid path in the band (dtw.cpp:211-213)
+  // Traceback (dtw.cpp:211-227).  The chain "record of row r -> column in row r-1" is sequential, but the record words
+  // it reads are not: all warps copy the words of a group of rows into shared memory at once (one global round trip
+  // per group instead of one per row: 18 % of the stall samples before, ncu profiles/r02f), then warp 0 walks the
+  // group from there.  Step r (R down to 1) turns the column of row r into the column of row r-1 with the records of
+  // row r-1; the virtual step R picks the end point: GetBestIndex on the last row (node.cpp:48-58), the first index
+  // of the row maximum = its last record.
+  uint32_t *stage = reinterpret_cast<uint32_t *>(smem + 16);  // the prefix-maximum rows are no longer needed
+  const int words_per_row = nch * NVB_WARP;
+  const bool staged = stage_words >= words_per_row;
+  const int group = staged ? min(64, stage_words / words_per_row) : 64;
+  int rel = 0;
+  bool no_path = false;
+  for (int hi = R - 1; hi >= 0; hi -= group) {
+    const int lo = max(0, hi - group + 1);
+    __syncthreads();
+    if (staged) {
+      const uint32_t *src = FL + (int64_t)lo * words_per_row;
+      for (int i = threadIdx.x; i < (hi - lo + 1) * words_per_row; i += blockDim.x) stage[i] = __ldcg(src + i);
+    }
+    __syncthreads();
+    if (warp != 0 || no_path) continue;
+    const uint32_t *rows0 = staged ? stage : FL + (int64_t)lo * words_per_row;
+    for (int r = hi + 1; r > lo; r--) {
+      int q;
+      if (r == R) {
+        int rs, re;
+        int64_t o;
+        row_geom2(v, mode, R - 1, rs, re, o);
+        q = re - rs;
+      } else {
+        int rs, re, ts, te;
+        int64_t o;
+        row_geom2(v, mode, r, rs, re, o);
+        const int col = rs + rel;
+        if (lane == 0) {
+          if (mode == NVB_MODE_TRANS) {
+            ev[r] = col;  // events[r/2][r%2]
+          } else {
+            ev[2 * (r - 1) + 1] = col;
+            if (r + 1 < R) ev[2 * r] = col;
+          }
+        }
+        const int mm = (mode == NVB_MODE_TRANS && ((r - 1) & 1)) ? 0 : B.mel;
+        row_geom2(v, mode, r - 1, ts, te, o);
+        q = min(col - mm, te) - ts;
+      }
+      rel = find_last_record<PK>(rows0 + (int64_t)(r - 1 - lo) * words_per_row, q, lane, false, 0);
+      if (r == R && rel < 0) { no_path = true; break; }  // no valid path in the band (dtw.cpp:211-213)
+    }
+  }
+  if (warp != 0) return;
+  if (no_path) {
     for (int i = lane; i < 2 * n; i += NVB_WARP) ev[i] = -1;
     if (lane == 0) status[b] = 1;
     return;
   }
-  // traceback (dtw.cpp:215-227); the record words of the next 8 rows above are fetched together
-  constexpr int G = 8;
-  for (int rt = R - 1; rt >= 0; rt -= G) {
-    uint32_t pre[G];
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-      const int rr = rt - g - 1;
-      pre[g] = (nch == 1 && rr >= 0) ? __ldcg(FL + (int64_t)rr * NVB_WARP + lane) : 0u;
-    }
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-      const int r = rt - g;
-      if (r < 0) break;
-      row_geom2(v, mode, r, rs, re, off);
-      const int col = rs + rel;
-      if (lane == 0) {
-        if (mode == NVB_MODE_TRANS) {
-          ev[r] = col;  // events[r/2][r%2]
-        } else {
-          if (r > 0) ev[2 * (r - 1) + 1] = col;
-          if (r + 1 < R) ev[2 * r] = col;
-        }
-      }
-      if (r > 0) {
-        const int m = (mode == NVB_MODE_TRANS && ((r - 1) & 1)) ? 0 : B.mel;
-        int qs, qe;
-        int64_t qoff;
-        row_geom2(v, mode, r - 1, qs, qe, qoff);
-        const int q = min(col - m, qe) - qs;
-        rel = find_last_record<PK>(FL + (int64_t)(r - 1) * nch * NVB_WARP, q, lane, nch == 1, pre[g]);
-      }
-    }
+  if (lane == 0) {  // row 0
+    int rs, re;
+    int64_t o;
+    row_geom2(v, mode, 0, rs, re, o);
+    const int col = rs + rel;
+    if (mode == NVB_MODE_TRANS) ev[0] = col;
+    else if (R > 1) ev[0] = col;
+    status[b] = 0;
   }
-  if (lane == 0) status[b] = 0;
 }
 
 template <int PK>
@@ -239,17 +279,24 @@ int launch_path(const BatchDev &B, int mode, int b0, int n_items, const int64_t 
   // warps per read: one per chunk of the widest row, at most 8 (wider rows take several rounds)
   int warps = (wave_maxw + PK * NVB_WARP - 1) / (PK * NVB_WARP);
   warps = warps < 1 ? 1 : (warps > 8 ? 8 : warps);
-  // shared memory: the chunk maxima and two prefix-maximum rows; global scratch rows for very wide bands
+  // shared memory: the chunk maxima, then two prefix-maximum rows (global scratch rows for very wide bands), reused by
+  // the traceback as a staging area for the record words of up to 64 rows
+  const int nch = (wave_maxw + PK * NVB_WARP - 1) / (PK * NVB_WARP);
+  const size_t want_stage = (size_t)32 * nch * NVB_WARP * sizeof(uint32_t);
   int smem_width = wave_maxw;
-  size_t smem = 16 * sizeof(double) + (size_t)2 * wave_maxw * sizeof(double);
-  if (smem > 200 * 1024) { smem_width = 0; smem = 16 * sizeof(double); }
+  size_t rows_bytes = (size_t)2 * wave_maxw * sizeof(double);
+  if (rows_bytes > 200 * 1024) { smem_width = 0; rows_bytes = 0; }
+  size_t body = rows_bytes > want_stage ? rows_bytes : want_stage;
+  if (body > 200 * 1024) body = rows_bytes;
+  const size_t smem = 16 * sizeof(double) + body;
+  const int stage_words = (int)(body / sizeof(uint32_t));
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(path2_kernel<PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return -1;
   }
   path2_kernel<PK><<<n_items, warps * NVB_WARP, smem, st>>>(B, mode, b0, n_items, d_mat_base, score, d_records,
-                                                             d_rec_base, d_dp, d_dp_base, smem_width, d_events,
-                                                             d_status);
+                                                             d_rec_base, d_dp, d_dp_base, smem_width, stage_words,
+                                                             d_events, d_status);
   return 0;
 }
 
