@@ -45,17 +45,16 @@ __device__ __forceinline__ double warp_excl_max(double x, int lane) {
 }
 
 // Last record bit at relative index <= t of a row whose record words start at `fl` (chunks of 32 words, PK columns
-// per word).  `w0` is the already loaded word of this lane for chunk t / (32 PK) when have_w0.  Returns -1 when there
-// is none.  Called by one whole warp.
+// per word).  Returns -1 when there is none.  Called by one whole warp.
 template <int PK>
-__device__ __forceinline__ int find_last_record(const uint32_t *fl, int t, int lane, bool have_w0, uint32_t w0) {
+__device__ __forceinline__ int find_last_record(const uint32_t *fl, bool in_smem, int t, int lane) {
   constexpr int PCH = PK * NVB_WARP;
   if (t < 0) return -1;
   int ch = t / PCH;
   int tl = t - ch * PCH;
   for (;;) {
-    uint32_t w = have_w0 ? w0 : __ldcg(fl + ch * NVB_WARP + lane);
-    have_w0 = false;
+    // staged rows are read from shared memory; unstaged ones (rows too wide to stage) straight from L2
+    uint32_t w = in_smem ? fl[ch * NVB_WARP + lane] : __ldcg(fl + ch * NVB_WARP + lane);
     const int lane_t = tl / PK, bit_t = tl - lane_t * PK;
     if (lane > lane_t) w = 0;
     else if (lane == lane_t) w &= (2u << bit_t) - 1u;
@@ -251,7 +250,7 @@ __global__ void __launch_bounds__(256) path2_kernel(BatchDev B, int mode, int b0
         row_geom2(v, mode, r - 1, ts, te, o);
         q = min(col - mm, te) - ts;
       }
-      rel = find_last_record<PK>(rows0 + (int64_t)(r - 1 - lo) * words_per_row, q, lane, false, 0);
+      rel = find_last_record<PK>(rows0 + (int64_t)(r - 1 - lo) * words_per_row, staged, q, lane);
       if (r == R && rel < 0) { no_path = true; break; }  // no valid path in the band (dtw.cpp:211-213)
     }
   }
