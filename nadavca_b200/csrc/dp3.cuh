@@ -81,6 +81,33 @@ __device__ __forceinline__ void exp_table_init() {
   __syncthreads();
 }
 
+#ifndef NVB_EXP_TABLE
+#define NVB_EXP_TABLE 1
+#endif
+
+#if !NVB_EXP_TABLE
+// The single-interval form (round 1): Cody-Waite against ln2 and a degree-13 Taylor polynomial on |r| <= 0.347
+// (error < 5e-18), p in [0.70, 1.42].  No table, 13 dependent DFMAs.
+#define NVB_LOG2E 1.44269504088896338700e+00
+static __constant__ double c_exp_poly13[11] = {
+    1.6059043836821613e-10, 2.08767569878681e-09,   2.505210838544172e-08,  2.755731922398589e-07,
+    2.7557319223985893e-06, 2.48015873015873e-05,   1.984126984126984e-04,  1.388888888888889e-03,
+    8.333333333333333e-03,  4.1666666666666664e-02, 1.6666666666666666e-01};
+__device__ __forceinline__ void exp_ext(double l, double &p, int &k) {
+  const double magic = 6755399441055744.0;
+  double t = fma(l, NVB_LOG2E, magic);
+  k = __double2loint(t);
+  double kd = t - magic;
+  double r = fma(-kd, NVB_LN2_HI, l);
+  r = fma(-kd, NVB_LN2_LO, r);
+  double q = c_exp_poly13[0];
+#pragma unroll
+  for (int i = 1; i < 11; i++) q = fma(q, r, c_exp_poly13[i]);
+  q = fma(q, r, 0.5);
+  q = fma(q, r, 1.0);
+  p = fma(q, r, 1.0);
+}
+#else
 __device__ __forceinline__ void exp_ext(double l, double &p, int &k) {
   const double magic = 6755399441055744.0;  // 1.5 * 2^52: rint via add/sub, integer in the low word
   const double t = fma(l, NVB_32_LOG2E, magic);
@@ -98,6 +125,7 @@ __device__ __forceinline__ void exp_ext(double l, double &p, int &k) {
   q *= r;             // exp(r) - 1
   p = fma(T, q, T);
 }
+#endif
 
 // natural log of f * 2^E (f > 0), E*ln2 added in two pieces
 __device__ __forceinline__ double log_ext(double f, int E) {

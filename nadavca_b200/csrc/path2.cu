@@ -302,8 +302,9 @@ int launch_path(const BatchDev &B, int mode, int b0, int n_items, const int64_t 
 }  // namespace
 
 // Columns per lane of the path search for a batch whose widest band row has `maxw` columns: 4 warps cover rows of
-// up to 384 columns at 3 per lane, 768 at 6; wider rows use 11 per lane and up to 8 warps.
-int nvbk_path2_columns_per_lane(int maxw) { return maxw <= 384 ? 3 : (maxw <= 768 ? 6 : 11); }
+// up to 384 columns at 3 per lane, 8 warps 1536 columns at 6; wider rows use 11 per lane (8 warps: 2816 columns per
+// round).
+int nvbk_path2_columns_per_lane(int maxw) { return maxw <= 384 ? 3 : (maxw <= 1536 ? 6 : 11); }
 
 void nvbk_score(int64_t total_cells, double *pF, const int32_t *pX, const double *sF, const int32_t *sX,
                 cudaStream_t st) {

@@ -111,15 +111,8 @@ def fit_spline(event_means, expected_means):
     return interpolate.splrep(means, expected, s=len(means))
 
 
-def _fit_spline_job(job):
-    return fit_spline(*job)
-
-
-_FIT_POOL = None
-
-
 class _Ready:
-    """Result holder with the ``get()`` of multiprocessing's AsyncResult."""
+    """Result holder with the ``get()`` of the pool's result handle."""
 
     def __init__(self, value):
         self.value = value
@@ -128,14 +121,91 @@ class _Ready:
         return self.value
 
 
+class _FitPool:
+    """Persistent pool of ``nadavca_b200.fit_worker`` subprocesses.  Plain subprocesses talking pickle over pipes:
+    unlike multiprocessing's spawn / forkserver workers they do not re-import the caller's ``__main__`` (an unguarded
+    script would run again in every worker) and they never inherit this process's CUDA context."""
+
+    def __init__(self, workers):
+        import os
+        import subprocess
+        import sys
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get('PYTHONPATH', ''),
+                   OMP_NUM_THREADS='1', OPENBLAS_NUM_THREADS='1', MKL_NUM_THREADS='1')
+        self.procs = [subprocess.Popen([sys.executable, '-m', 'nadavca_b200.fit_worker'], stdin=subprocess.PIPE,
+                                       stdout=subprocess.PIPE, env=env) for _ in range(workers)]
+        self.pending = []  # submitted, not yet collected: results come back through the pipes in this order
+
+    def submit(self, jobs):
+        """Deal the jobs to the workers in contiguous shares; returns a handle with ``get()``."""
+        import pickle
+        import struct
+        n = len(self.procs)
+        bounds = [len(jobs) * i // n for i in range(n + 1)]
+        used = []
+        for proc, lo, hi in zip(self.procs, bounds[:-1], bounds[1:]):
+            if hi > lo:
+                blob = pickle.dumps(jobs[lo:hi], protocol=pickle.HIGHEST_PROTOCOL)
+                proc.stdin.write(struct.pack('<q', len(blob)))
+                proc.stdin.write(blob)
+                proc.stdin.flush()
+                used.append(proc)
+        handle = _PoolResult(self, used)
+        self.pending.append(handle)
+        return handle
+
+    def close(self):
+        for proc in self.procs:
+            try:
+                proc.stdin.close()
+                proc.terminate()
+            except Exception:
+                pass
+
+
+class _PoolResult:
+    def __init__(self, pool, procs):
+        self.pool, self.procs, self.value, self.error = pool, procs, None, None
+
+    def get(self):
+        while self.value is None and self.error is None:
+            self.pool.pending.pop(0)._collect()  # earlier submissions first: the pipes are FIFO
+        if self.error:
+            raise RuntimeError('spline fit failed in a worker: {}'.format(self.error))
+        return self.value
+
+    def _collect(self):
+        import pickle
+        import struct
+        if self.value is None:
+            out = []
+            error = None
+            for proc in self.procs:
+                head = proc.stdout.read(8)
+                if len(head) < 8:
+                    error = error or 'a spline-fit worker died'
+                    continue
+                status, payload = pickle.loads(proc.stdout.read(struct.unpack('<q', head)[0]))
+                if status == 'ok':
+                    out.extend(payload)
+                else:
+                    error = error or payload
+            self.error = error
+            self.value = out
+
+
+_FIT_POOL = None
+
+
 def fit_splines_async(jobs, workers=None):
-    """``fit_spline`` for many reads; returns a handle whose ``get()`` gives the list of splines.  The FITPACK fit is host work that the reference does one read at a time
-    (0.3-1 ms each, holding the GIL); batches of 32 reads or more go through a persistent pool of worker processes
-    (``forkserver``: the workers never see this process's CUDA context), which runs the SAME scipy call, so the
-    splines are identical.  NADAVCA_FIT_WORKERS=0 disables the pool."""
+    """``fit_spline`` for many reads; returns a handle whose ``get()`` gives the list of splines.  The FITPACK fit is
+    host work that the reference does one read at a time (0.3-1 ms each, holding the GIL: threads do not help);
+    batches of 32 reads or more go through a persistent pool of worker processes, which run the SAME scipy call, so
+    the splines are identical.  NADAVCA_FIT_WORKERS=0 disables the pool."""
     global _FIT_POOL
     import os
-    jobs = list(jobs)
+    jobs = [(numpy.asarray(m, dtype=float), numpy.asarray(e, dtype=float)) for m, e in jobs]
     if workers is None:
         workers = int(os.environ.get('NADAVCA_FIT_WORKERS', min(32, max(1, (os.cpu_count() or 1) //
                                                                         int(os.environ.get('LOCAL_WORLD_SIZE', '1'))))))
@@ -143,13 +213,12 @@ def fit_splines_async(jobs, workers=None):
         return _Ready([fit_spline(*job) for job in jobs])
     if _FIT_POOL is None or _FIT_POOL[1] != workers:
         import atexit
-        import multiprocessing
         if _FIT_POOL is not None:
-            _FIT_POOL[0].terminate()
-        pool = multiprocessing.get_context('forkserver').Pool(workers)
-        atexit.register(pool.terminate)
+            _FIT_POOL[0].close()
+        pool = _FitPool(workers)
+        atexit.register(pool.close)
         _FIT_POOL = (pool, workers)
-    return _FIT_POOL[0].map_async(_fit_spline_job, jobs, chunksize=max(1, len(jobs) // (4 * workers)))
+    return _FIT_POOL[0].submit(jobs)
 
 
 def _normalize_on_device(values, device, process_group=None):
