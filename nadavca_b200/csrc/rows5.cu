@@ -23,14 +23,18 @@ namespace {
 #define NVB_ROT_MIN_BLOCKS 8  // 64-thread CTAs per SM: 128 registers per thread, 16 warps per SM
 #endif
 
-#ifndef NVB_ROT_TS
-#define NVB_ROT_TS 8
+// Steps per store tile; pairs are (de)activated only at multiples of it.  The per-tile work (slot management, ring
+// upkeep, the transposing flush: ~300 warp instructions) is amortised over the tile, but a coarser tile keeps pairs in
+// their slots longer, so the second slot -- which makes the whole warp run the step body twice -- is live more often.
+// Measured at 1000 reads (profiles/r02e): 8 steps win for the plain sweep (18.4 -> 16.6 ms), 4 for the wobble sweep
+// (25.6 against 26.7 ms).  8 is the largest value the slot-reuse guarantee of band.cu (be[j] - bs[j+63] <= 48) allows.
+#ifndef NVB_ROT_TS_PLAIN
+#define NVB_ROT_TS_PLAIN 8
 #endif
-// Steps per store tile; pairs are (de)activated only at multiples of TS.  The per-tile work (slot management, ring
-// upkeep, the transposing flush: ~300 warp instructions) is amortised over TS steps; 8 is the largest value the
-// slot-reuse guarantee of band.cu (be[j] - bs[j+63] <= 48) allows.
-constexpr int TS = NVB_ROT_TS;
-constexpr int TSTRIDE = TS + 1;  // padded tile row stride
+#ifndef NVB_ROT_TS_OTHER
+#define NVB_ROT_TS_OTHER 4
+#endif
+__host__ __device__ constexpr int tile_steps(int mode) { return mode == NVB_MODE_PLAIN ? NVB_ROT_TS_PLAIN : NVB_ROT_TS_OTHER; }
 
 struct RowMeta {
   long long off;  // offset of the row's first cell in the matrix planes
@@ -39,19 +43,22 @@ struct RowMeta {
   int pad;
 };
 struct StoreTile {
-  double *f;      // [32][TSTRIDE]
-  int32_t *x;     // [32][TSTRIDE]
+  double *f;      // [32][TS + 1]
+  int32_t *x;     // [32][TS + 1]
   RowMeta *meta;  // [32]
 };
-constexpr size_t kTileBytes = 32 * TSTRIDE * (sizeof(double) + sizeof(int32_t)) + 32 * sizeof(RowMeta);
+__host__ __device__ constexpr size_t tile_bytes(int ts) {
+  return 32 * (ts + 1) * (sizeof(double) + sizeof(int32_t)) + 32 * sizeof(RowMeta);
+}
 // tiles per warp: the B rows of the two slots, plus their A rows in the transition sweep (the only one that stores them)
 __host__ __device__ constexpr int tiles_per_warp(int mode) { return mode == NVB_MODE_TRANS ? 4 : 2; }
 __host__ __device__ constexpr size_t warp_bytes(int mode) {  // keeps every ring 256-byte aligned
-  return ((tiles_per_warp(mode) * kTileBytes + ring_bytes(8) + 255) / 256) * 256;
+  return ((tiles_per_warp(mode) * tile_bytes(tile_steps(mode)) + ring_bytes(8) + 255) / 256) * 256;
 }
 
-template <bool REV>
+template <bool REV, int TS>
 __device__ __forceinline__ void flush_tile(const StoreTile &tile, double *F, int32_t *X, int C0, int t0, int lane) {
+  constexpr int TSTRIDE = TS + 1;     // padded tile row stride
   constexpr int RPI = NVB_WARP / TS;  // rows per iteration
   const int kk = lane & (TS - 1);
 #pragma unroll
@@ -208,6 +215,7 @@ __device__ void sweep_rotate(const ModelDev &M, const ReadView &v, double *F, in
                              const StoreTile (&tiles)[4], const SignalRing<8> &R) {
   const int n = v.n;
   constexpr bool TRANS = (MODE == NVB_MODE_TRANS);
+  constexpr int TS = tile_steps(MODE), TSTRIDE = TS + 1;
   // tiles: B rows of slot P and slot Q2, then (transition sweep only) their A rows
   const StoreTile &tPB = tiles[0], &tSB = tiles[1], &tPA = tiles[TRANS ? 2 : 0], &tSA = tiles[TRANS ? 3 : 1];
 
@@ -290,11 +298,11 @@ __device__ void sweep_rotate(const ModelDev &M, const ReadView &v, double *F, in
     }
     if (k == TS - 1) {
       __syncwarp();
-      flush_tile<REV>(tPB, F, X, C0, t - k, lane);
-      if (TRANS) flush_tile<REV>(tPA, F, X, C0, t - k, lane);
+      flush_tile<REV, TS>(tPB, F, X, C0, t - k, lane);
+      if (TRANS) flush_tile<REV, TS>(tPA, F, X, C0, t - k, lane);
       if (any2_tile) {
-        flush_tile<REV>(tSB, F, X, C0, t - k, lane);
-        if (TRANS) flush_tile<REV>(tSA, F, X, C0, t - k, lane);
+        flush_tile<REV, TS>(tSB, F, X, C0, t - k, lane);
+        if (TRANS) flush_tile<REV, TS>(tSA, F, X, C0, t - k, lane);
       }
       __syncwarp();
     }
@@ -321,16 +329,16 @@ __global__ void __launch_bounds__(64, NVB_ROT_MIN_BLOCKS) sweep5_kernel(ModelDev
   StoreTile tiles[4];
 #pragma unroll
   for (int i = 0; i < tiles_per_warp(MODE); i++) {
-    unsigned char *p = base + (size_t)i * kTileBytes;
+    unsigned char *p = base + (size_t)i * tile_bytes(tile_steps(MODE));
     tiles[i].f = reinterpret_cast<double *>(p);
-    tiles[i].meta = reinterpret_cast<RowMeta *>(tiles[i].f + 32 * TSTRIDE);
+    tiles[i].meta = reinterpret_cast<RowMeta *>(tiles[i].f + 32 * (tile_steps(MODE) + 1));
     tiles[i].x = reinterpret_cast<int32_t *>(tiles[i].meta + 32);
   }
   ReadView v = read_view(B, b);
   const int64_t mb = mat_base[b];
   // signal ring (dp3.cuh) behind the four store tiles: 8 chunks of 32 samples + 8 mbarriers, filled by TMA bulk copies
   SignalRing<8> R;
-  ring_init(R, base + tiles_per_warp(MODE) * kTileBytes, B.signal, B.sig_off[b], B.sig_off[B.n_reads], lane);
+  ring_init(R, base + tiles_per_warp(MODE) * tile_bytes(tile_steps(MODE)), B.signal, B.sig_off[b], B.sig_off[B.n_reads], lane);
   if (item & 1) sweep_rotate<MEL, MODE, true>(M, v, sF + mb, sX + mb, lane, tiles, R);
   else sweep_rotate<MEL, MODE, false>(M, v, pF + mb, pX + mb, lane, tiles, R);
 }
