@@ -72,17 +72,33 @@ __device__ __forceinline__ int find_last_record(const uint32_t *fl, bool in_smem
 // One CTA per read, NWP = blockDim.x / 32 warps.  A row is cut into chunks of 32 * PK consecutive columns (PK per
 // lane); chunk ch of a row is worked by warp ch % NWP, all chunks of a round of NWP at the same time: each warp scans
 // its chunk, publishes the chunk maximum, and after a CTA barrier takes the maximum of the chunks in front of it as
-// its carry.  Rows are inherently sequential (dp[r] needs the prefix maxima of dp[r-1]); what the extra warps buy is a
-// row in ~1/NWP of the instructions per warp -- the kernel is bound by the dependent-issue latency of one warp
-// (ncu, profiles/r01e: 870 warp instructions per 301-column row at PK = 11, 3.3 us per row).
-template <int PK>
+// its carry.  Rows are inherently sequential (dp[r] needs the prefix maxima of dp[r-1]); the kernel is bound by the
+// dependent-issue latency of one row, so everything that is not the recurrence is kept off it:
+//   * band geometry (start, end, offset of every row) is computed GB rows at a time into a shared-memory table
+//     (ncu profiles/r02f: 472 warp instructions per row and warp, most of them geometry arithmetic and loads);
+//   * the scores of row r+D are copied global -> shared with cp.async while row r is worked (no registers, no
+//     stall on first use: 21 % of the stall samples with a one-row register prefetch);
+//   * the traceback stages the record words AND the geometry of 64 rows at a time (all warps), then warp 0 walks them.
+constexpr int GB = 64;  // rows per geometry block
+
+struct RowGeo {
+  int s, e;
+  long long off;
+};
+
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
+}
+
+template <int PK, int D>
 __global__ void __launch_bounds__(256) path2_kernel(BatchDev B, int mode, int b0, int n_items, const int64_t *mat_base,
                                                     const double *score, uint32_t *records, const int64_t *rec_base,
                                                     double *gscratch, const int64_t *dp_base, int smem_width,
                                                     int stage_words, int32_t *events, int32_t *status) {
   extern __shared__ double smem[];
   constexpr int PCH = PK * NVB_WARP;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NWP = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NWP = blockDim.x >> 5, NT = blockDim.x;
   const int item = blockIdx.x;
   if (item >= n_items) return;
   const int b = b0 + item;
@@ -100,42 +116,64 @@ __global__ void __launch_bounds__(256) path2_kernel(BatchDev B, int mode, int b0
   const int nch = (maxw + PCH - 1) / PCH;
   const double *SC = score + mat_base[b];
   uint32_t *FL = records + rec_base[b];
-  double *tot = smem;  // [2][8]: chunk maxima of the current round, double buffered over rounds
+  // shared memory: chunk maxima [2][8] | geometry table [GB + D + 1] | score ring [D][NT * PK] | two prefix-max rows
+  double *tot = smem;
+  RowGeo *geo = reinterpret_cast<RowGeo *>(smem + 16);
+  double *ring = smem + 16 + 2 * (GB + D + 1);
+  double *body = ring + (size_t)D * NT * PK;  // also the staging area of the traceback
   double *Mprev, *Mcur;
-  if (smem_width > 0) { Mprev = smem + 16; Mcur = Mprev + smem_width; }
+  if (smem_width > 0) { Mprev = body; Mcur = Mprev + smem_width; }
   else { Mprev = gscratch + dp_base[b]; Mcur = Mprev + maxw; }
 
-  // Rows in flight: geometry and this warp's first-chunk scores of rows r .. r+D-1 are requested D rows ahead (one row
-  // of work is shorter than a global-load round trip: with a single row of look-ahead 21 % of the stall samples were
-  // the first use of the prefetched scores, ncu profiles/r02f).  Slot 0 is the current row.
-  constexpr int D = PK <= 3 ? 4 : (PK <= 6 ? 2 : 1);
-  int qs[D + 1], qe[D + 1];
-  double qsc[D + 1][PK];
-  auto fetch = [&](int slot, int r) {
-    qs[slot] = 0; qe[slot] = -1;
-    if (r < R) {
-      int64_t o;
-      row_geom2(v, mode, r, qs[slot], qe[slot], o);
-      const int c0 = qs[slot] + warp * PCH + lane * PK;
-#pragma unroll
-      for (int j = 0; j < PK; j++)
-        qsc[slot][j] = (c0 + j <= qe[slot]) ? __ldg(SC + o + (c0 + j - qs[slot])) : NINF;
-    } else {
-#pragma unroll
-      for (int j = 0; j < PK; j++) qsc[slot][j] = NINF;
+  int gbase = 0;
+  auto fill_geo = [&](int base, int count) {  // rows base .. base+count-1 into geo[0 .. count)
+    for (int i = threadIdx.x; i < count; i += NT) {
+      RowGeo g;
+      g.s = 0; g.e = -1; g.off = 0;
+      if (base + i >= 0 && base + i < R) {
+        int64_t o;
+        row_geom2(v, mode, base + i, g.s, g.e, o);
+        g.off = o;
+      }
+      geo[i] = g;
     }
   };
+  // this thread's PK scores of row r (first round of chunks) -> ring slot r % D
+  auto request = [&](int r) {
+    double *dst = ring + (size_t)(r % D) * NT * PK + threadIdx.x * PK;
+    const RowGeo g = geo[r - gbase];
+    const int c0 = g.s + warp * PCH + lane * PK;
 #pragma unroll
-  for (int d = 0; d < D; d++) fetch(d, d);
+    for (int j = 0; j < PK; j++) {
+      if (r < R && c0 + j <= g.e) cp_async8(dst + j, SC + g.off + (c0 + j - g.s));
+      else dst[j] = NINF;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fill_geo(0, GB + D + 1);
+  __syncthreads();
+#pragma unroll
+  for (int d = 0; d < D; d++) request(d);
+
   int ps = 0, pe = -1;
   int flip = 0;
   for (int r = 0; r < R; r++) {
+    if (r - gbase == GB) {  // next geometry block (the end-of-row barrier of row r-1 separates it from the readers)
+      gbase = r;
+      fill_geo(gbase, GB + D + 1);
+      __syncthreads();
+    }
     const int m = (r == 0) ? 0 : ((mode == NVB_MODE_TRANS && ((r - 1) & 1)) ? 0 : B.mel);  // dtw.cpp:165-179
-    fetch(D, r + D);
-    const int s = qs[0], e = qe[0];
+    const RowGeo g = geo[r - gbase];
+    const int s = g.s, e = g.e;
+    asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");  // this thread's scores of row r have landed
     double cur[PK];
+    {
+      const double *src = ring + (size_t)(r % D) * NT * PK + threadIdx.x * PK;
 #pragma unroll
-    for (int j = 0; j < PK; j++) cur[j] = qsc[0][j];
+      for (int j = 0; j < PK; j++) cur[j] = src[j];
+    }
+    request(r + D);  // into the slot just read (own elements only)
     const int w = e - s + 1;
     double round_carry = NINF;  // maximum over all chunks of the rounds before this one
     for (int base = 0; base * PCH < w; base += NWP) {
@@ -146,12 +184,7 @@ __global__ void __launch_bounds__(256) path2_kernel(BatchDev B, int mode, int b0
       for (int j = 0; j < PK; j++) {
         const int c = c0 + j;
         double sc = cur[j];
-        if (base > 0) {  // rows wider than NWP chunks: later rounds load their scores directly
-          int ts, te;
-          int64_t off;
-          row_geom2(v, mode, r, ts, te, off);
-          sc = (c <= e) ? __ldg(SC + off + (c - s)) : NINF;
-        }
+        if (base > 0) sc = (c <= e) ? __ldg(SC + g.off + (c - s)) : NINF;  // rows wider than NWP chunks: later rounds
         if (r > 0) {
           // best predecessor over i' <= c - m inside the previous row's band (node.cpp:68-89)
           const int q = c - m;
@@ -185,40 +218,37 @@ __global__ void __launch_bounds__(256) path2_kernel(BatchDev B, int mode, int b0
       }
       if (ch < nch) FL[((int64_t)r * nch + ch) * NVB_WARP + lane] = bits;
       if (NWP > 1) {
-        for (int k = 0; k < NWP; k++) round_carry = fmax(round_carry, T[k]);
+        if (w > NWP * PCH) {  // more rounds follow
+          for (int k = 0; k < NWP; k++) round_carry = fmax(round_carry, T[k]);
+        }
         flip ^= 1;
       } else {
         round_carry = __shfl_sync(NVB_FULL, before, NVB_WARP - 1);
       }
     }
-    __syncthreads();  // Mcur is complete: the next row reads it as Mprev (one warp per read: a warp barrier would do)
+    __syncthreads();  // Mcur is complete: the next row reads it as Mprev
     double *t = Mprev; Mprev = Mcur; Mcur = t;
     ps = s; pe = e;
-#pragma unroll
-    for (int d = 0; d < D; d++) {
-      qs[d] = qs[d + 1]; qe[d] = qe[d + 1];
-#pragma unroll
-      for (int j = 0; j < PK; j++) qsc[d][j] = qsc[d + 1][j];
-    }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __threadfence_block();
   __syncthreads();
 
-  // Traceback (dtw.cpp:211-227).  The chain "record of row r -> column in row r-1" is sequential, but the record words
-  // it reads are not: all warps copy the words of a group of rows into shared memory at once (one global round trip
-  // per group instead of one per row: 18 % of the stall samples before, ncu profiles/r02f), then warp 0 walks the
-  // group from there.  Step r (R down to 1) turns the column of row r into the column of row r-1 with the records of
-  // row r-1; the virtual step R picks the end point: GetBestIndex on the last row (node.cpp:48-58), the first index
-  // of the row maximum = its last record.
-  uint32_t *stage = reinterpret_cast<uint32_t *>(smem + 16);  // the prefix-maximum rows are no longer needed
+  // Traceback (dtw.cpp:211-227).  The chain "record of row r -> column in row r-1" is sequential, but what it reads is
+  // not: all warps copy the record words and the geometry of a group of rows into shared memory at once (one global
+  // round trip per group instead of several per row), then warp 0 walks the group from there.  Step r (R down to 1)
+  // turns the column of row r into the column of row r-1 with the records of row r-1; the virtual step R picks the end
+  // point: GetBestIndex on the last row (node.cpp:48-58), the first index of the row maximum = its last record.
+  uint32_t *stage = reinterpret_cast<uint32_t *>(body);
   const int words_per_row = nch * NVB_WARP;
   const bool staged = stage_words >= words_per_row;
-  const int group = staged ? min(64, stage_words / words_per_row) : 64;
+  const int group = staged ? min(GB, stage_words / words_per_row) : GB;
   int rel = 0;
   bool no_path = false;
   for (int hi = R - 1; hi >= 0; hi -= group) {
     const int lo = max(0, hi - group + 1);
     __syncthreads();
+    fill_geo(lo, hi - lo + 2);  // geo[i] = row lo + i, up to row hi + 1 (empty when hi + 1 == R)
     if (staged) {
       const uint32_t *src = FL + (int64_t)lo * words_per_row;
       for (int i = threadIdx.x; i < (hi - lo + 1) * words_per_row; i += blockDim.x) stage[i] = __ldcg(src + i);
@@ -228,16 +258,11 @@ __global__ void __launch_bounds__(256) path2_kernel(BatchDev B, int mode, int b0
     const uint32_t *rows0 = staged ? stage : FL + (int64_t)lo * words_per_row;
     for (int r = hi + 1; r > lo; r--) {
       int q;
+      const RowGeo below = geo[r - 1 - lo];  // row r-1
       if (r == R) {
-        int rs, re;
-        int64_t o;
-        row_geom2(v, mode, R - 1, rs, re, o);
-        q = re - rs;
+        q = below.e - below.s;
       } else {
-        int rs, re, ts, te;
-        int64_t o;
-        row_geom2(v, mode, r, rs, re, o);
-        const int col = rs + rel;
+        const int col = geo[r - lo].s + rel;
         if (lane == 0) {
           if (mode == NVB_MODE_TRANS) {
             ev[r] = col;  // events[r/2][r%2]
@@ -247,8 +272,7 @@ __global__ void __launch_bounds__(256) path2_kernel(BatchDev B, int mode, int b0
           }
         }
         const int mm = (mode == NVB_MODE_TRANS && ((r - 1) & 1)) ? 0 : B.mel;
-        row_geom2(v, mode, r - 1, ts, te, o);
-        q = min(col - mm, te) - ts;
+        q = min(col - mm, below.e) - below.s;
       }
       rel = find_last_record<PK>(rows0 + (int64_t)(r - 1 - lo) * words_per_row, staged, q, lane);
       if (r == R && rel < 0) { no_path = true; break; }  // no valid path in the band (dtw.cpp:211-213)
@@ -271,31 +295,32 @@ __global__ void __launch_bounds__(256) path2_kernel(BatchDev B, int mode, int b0
   }
 }
 
-template <int PK>
+template <int PK, int D>
 int launch_path(const BatchDev &B, int mode, int b0, int n_items, const int64_t *d_mat_base, const double *score,
                 uint32_t *d_records, const int64_t *d_rec_base, double *d_dp, const int64_t *d_dp_base, int wave_maxw,
                 int32_t *d_events, int32_t *d_status, cudaStream_t st) {
   // warps per read: one per chunk of the widest row, at most 8 (wider rows take several rounds)
   int warps = (wave_maxw + PK * NVB_WARP - 1) / (PK * NVB_WARP);
   warps = warps < 1 ? 1 : (warps > 8 ? 8 : warps);
-  // shared memory: the chunk maxima, then two prefix-maximum rows (global scratch rows for very wide bands), reused by
-  // the traceback as a staging area for the record words of up to 64 rows
   const int nch = (wave_maxw + PK * NVB_WARP - 1) / (PK * NVB_WARP);
+  // shared memory: chunk maxima, geometry table, score ring, then two prefix-maximum rows (global scratch rows for
+  // very wide bands), reused by the traceback as a staging area for the record words of up to GB rows
+  const size_t head = (16 + 2 * (GB + D + 1) + (size_t)D * warps * NVB_WARP * PK) * sizeof(double);
   const size_t want_stage = (size_t)32 * nch * NVB_WARP * sizeof(uint32_t);
   int smem_width = wave_maxw;
   size_t rows_bytes = (size_t)2 * wave_maxw * sizeof(double);
-  if (rows_bytes > 200 * 1024) { smem_width = 0; rows_bytes = 0; }
+  if (head + rows_bytes > 200 * 1024) { smem_width = 0; rows_bytes = 0; }
   size_t body = rows_bytes > want_stage ? rows_bytes : want_stage;
-  if (body > 200 * 1024) body = rows_bytes;
-  const size_t smem = 16 * sizeof(double) + body;
+  if (head + body > 200 * 1024) body = rows_bytes;
+  const size_t smem = head + body;
   const int stage_words = (int)(body / sizeof(uint32_t));
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(path2_kernel<PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(path2_kernel<PK, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return -1;
   }
-  path2_kernel<PK><<<n_items, warps * NVB_WARP, smem, st>>>(B, mode, b0, n_items, d_mat_base, score, d_records,
-                                                             d_rec_base, d_dp, d_dp_base, smem_width, stage_words,
-                                                             d_events, d_status);
+  path2_kernel<PK, D><<<n_items, warps * NVB_WARP, smem, st>>>(B, mode, b0, n_items, d_mat_base, score, d_records,
+                                                                d_rec_base, d_dp, d_dp_base, smem_width, stage_words,
+                                                                d_events, d_status);
   return 0;
 }
 
@@ -322,8 +347,8 @@ int nvbk_path2(const BatchDev &B, int mode, int b0, int b1, int pk, const int64_
   const int n_items = b1 - b0;
   if (n_items <= 0) return 0;
   switch (pk) {
-    case 3: return launch_path<3>(B, mode, b0, n_items, d_mat_base, score, d_records, d_rec_base, d_dp, d_dp_base, wave_maxw, d_events, d_status, st);
-    case 6: return launch_path<6>(B, mode, b0, n_items, d_mat_base, score, d_records, d_rec_base, d_dp, d_dp_base, wave_maxw, d_events, d_status, st);
-    default: return launch_path<11>(B, mode, b0, n_items, d_mat_base, score, d_records, d_rec_base, d_dp, d_dp_base, wave_maxw, d_events, d_status, st);
+    case 3: return launch_path<3, 4>(B, mode, b0, n_items, d_mat_base, score, d_records, d_rec_base, d_dp, d_dp_base, wave_maxw, d_events, d_status, st);
+    case 6: return launch_path<6, 3>(B, mode, b0, n_items, d_mat_base, score, d_records, d_rec_base, d_dp, d_dp_base, wave_maxw, d_events, d_status, st);
+    default: return launch_path<11, 2>(B, mode, b0, n_items, d_mat_base, score, d_records, d_rec_base, d_dp, d_dp_base, wave_maxw, d_events, d_status, st);
   }
 }
