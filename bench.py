@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument('--bandwidth', type=int, default=None, help='default 150 (400 for --config 3)')
     ap.add_argument('--cpu-sample', type=int, default=0, help='reads in the CPU sample (0 = one per host core)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-overlap', action='store_true', help='skip the two-stream pipeline measurement')
+    ap.add_argument('--no-overlap', action='store_true', help='accepted for older scripts; no effect')
     a = ap.parse_args()
     per_config = {0: (100, 2000, 150), 1: (1000, 2000, 150), 2: (1000, 2000, 150), 3: (62, 100_000, 400),
                   4: (None, 2000, 150)}[a.config]
@@ -471,40 +471,6 @@ def run_ours(args):
             'rows_sum_to_one_max_err': float((probs_c.sum(dim=1) - 1).abs().max().item()),
         }
 
-    # ---- software pipeline over consecutive batches (reported next to `value`, never instead of it) --------------
-    # In a job of many batches the refine stage of batch k+1 does not depend on the estimate stage of batch k.  With
-    # a second model handle (its own DP workspace) and two streams the latency-bound sweeps of one batch fill the
-    # issue slots the SNP kernel of the other leaves free.  Same kernels, same work per step.
-    overlap_ms = None
-    if not args.no_overlap:
-        km2 = load_model()
-        km2._device = local_rank
-        batch_n2 = dtw.Batch(km2, *lists, args.bandwidth, mel)
-        s_a, s_b = torch.cuda.Stream(), torch.cuda.Stream()
-
-        def overlapped_step():
-            batch_n2.refine(False, s_a)
-            batch_t.estimate(True, s_b)
-            with torch.cuda.stream(s_b):
-                est.posterior_stage(batch_t, reverse, intervals, genome, independent=True, plan=plan)
-
-        for _ in range(2):
-            overlapped_step()
-        barrier()
-        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        o0.record(stream)
-        s_a.wait_stream(stream)
-        s_b.wait_stream(stream)
-        for _ in range(args.steps):
-            overlapped_step()
-        stream.wait_stream(s_a)
-        stream.wait_stream(s_b)
-        o1.record(stream)
-        barrier()
-        overlap_ms = o0.elapsed_time(o1) / args.steps
-        batch_n2.close()
-        del km2
-
     # ---- end to end through the C ABI with pinned host buffers -----------------------------------------------
     def pinned(arr):
         t = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
@@ -589,7 +555,6 @@ def run_ours(args):
 
     # ---- reductions over ranks -----------------------------------------------------------------------------------
     ms_max = reduce_over_ranks(ms, 'max', dev)
-    overlap_max = None if overlap_ms is None else reduce_over_ranks(overlap_ms, 'max', dev)
     e2e_max = reduce_over_ranks(e2e_s, 'max', dev)
     samples_all = reduce_over_ranks(float(samples), 'sum', dev)
     cells_all = reduce_over_ranks(float(total_cells), 'sum', dev)
@@ -645,10 +610,6 @@ def run_ours(args):
                 nvlink_peak_GBs_per_direction=900.0,
                 workload='configs[2] shape: estimate_snps independent=False, %d reads per GPU over a %.1f Mb '
                          'synthetic genome; timed region includes the NCCL exchange' % (args.reads, args.genome / 1e6)),
-            'pipelined': None if overlap_max is None else {
-                'value': samples_all / (overlap_max * 1e-3), 'unit': 'samples/s', 'ms_per_step': overlap_max,
-                'how': 'refine of the next batch on a second stream / workspace while the current batch is in its '
-                       'estimate stage; same kernels and work per step as `value`'},
         }
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'], line['parity'] = cpu_baseline(km, items, tweaked, args, mel, gpu_events, gpu_ll)

@@ -145,8 +145,9 @@ __global__ void __launch_bounds__(256) path2_kernel(BatchDev B, int mode, int b0
     const int c0 = g.s + warp * PCH + lane * PK;
 #pragma unroll
     for (int j = 0; j < PK; j++) {
+      // columns outside the band are never copied: their slots hold stale values, which the consumer masks (a plain
+      // store here would have to wait for every cp.async in flight: 25 % of the stall samples, ncu profiles/r02m)
       if (r < R && c0 + j <= g.e) cp_async8(dst + j, SC + g.off + (c0 + j - g.s));
-      else dst[j] = NINF;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(256) path2_kernel(BatchDev B, int mode, int b0
 #pragma unroll
       for (int j = 0; j < PK; j++) {
         const int c = c0 + j;
-        double sc = cur[j];
+        double sc = (c <= e) ? cur[j] : NINF;  // (slots of columns outside the band hold stale values)
         if (base > 0) sc = (c <= e) ? __ldg(SC + g.off + (c - s)) : NINF;  // rows wider than NWP chunks: later rounds
         if (r > 0) {
           // best predecessor over i' <= c - m inside the previous row's band (node.cpp:68-89)

@@ -380,7 +380,10 @@ def test_bench_line_contract():
     assert set(line['roofline']) >= {'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'}
     assert line['roofline']['bound'] == 'hbm' and 0 < line['roofline']['frac'] < 1
     assert line['cpu_baseline']['kind'] in ('reference', 'port') and line['cpu_baseline']['cores'] >= 1
-    assert 'workload' in line['config'] and line['pipelined']['value'] > 0
+    assert 'workload' in line['config']
+    assert line['consensus']['ranks_identical'] and line['consensus']['value'] > 0
+    assert line['api']['estimate_snps']['value'] > 0 and line['api']['align_signal']['aligned'] == 24
+    assert 0 < line['alu']['issue_frac'] < 1
     # the benchmarked reads themselves are checked against the reference inside the CPU leg
     par = line['parity']
     assert par['reads'] == 2 and par['event_mismatches'] == 0 and par['ll_mismatches'] == 0
