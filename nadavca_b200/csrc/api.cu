@@ -303,9 +303,13 @@ nvb_model *nvb_model_create(int k, int central_position, int alphabet_size, cons
 
 void nvb_model_destroy(nvb_model *model) {
   if (!model) return;
-  cudaSetDevice(model->device);
+  const int device = model->device;
+  cudaSetDevice(device);
   cudaDeviceSynchronize();
   delete model;
+  // its workspaces (often several GB) went to the block cache: hand them back to the driver, other allocators
+  // (torch) may need the memory
+  pool_trim(device);
 }
 
 int nvb_model_k(const nvb_model *m) { return m ? m->dev.k : 0; }

@@ -56,8 +56,11 @@ __device__ __forceinline__ PairGeom pair_geom(const ReadView &v, int mode, int g
 // L1 hit rate of the signal loads 4 %) to be what the sweep waits for.  Instead every lane parks its cell in a
 // [32 rows][TS steps] tile and every TS steps the warp writes the tile out row segment by row segment: TS consecutive
 // threads write TS consecutive cells of one row.
-constexpr int TS = 4;        // steps per tile (4 keeps a CTA's shared memory small enough for 14 CTAs per SM)
-constexpr int TSTRIDE = 5;   // padded row stride (conflict-free for the per-step column writes)
+#ifndef NVB_STRIPE_TS
+#define NVB_STRIPE_TS 8
+#endif
+constexpr int TS = NVB_STRIPE_TS;  // steps per tile: the flush (~270 warp instructions per tile) is amortised over them
+constexpr int TSTRIDE = TS + 1;    // padded row stride (conflict-free for the per-step column writes)
 struct RowMeta {
   long long off;  // offset of the row's first cell in the matrix planes
   int s, e;       // band of the row (empty for lanes that store nothing)
