@@ -393,6 +393,10 @@ struct LaneOut {
 // The step comes in two halves so that the latency-bound sweeps can evaluate the emission of step t+1 (which depends
 // on nothing but the sample) while the state update of step t waits for its neighbour: lane_emit + lane_update.
 __device__ __forceinline__ void lane_emit(const LaneCfg &L, double x, double &p, int &kk) {
+#ifdef NVB_EXPERIMENT_NO_EMIT  // timing experiment only (wrong results): what a step costs without its emission
+  p = 1.0 + 1e-9 * x; kk = 0;
+  return;
+#endif
   // own emission, reference formula ac - d*d*mc (kmer_model.cpp:47-51)
   const double d = x - L.mu;
   const double l = L.ac - d * d * L.mc;

@@ -296,7 +296,11 @@ __device__ void sweep_rotate(const ModelDev &M, const ReadView &v, double *F, in
       tSB.x[lane * TSTRIDE + k] = Q2.out.E;
       if (TRANS) { tSA.f[lane * TSTRIDE + k] = Q2.aout.f; tSA.x[lane * TSTRIDE + k] = Q2.aout.e; }
     }
+#ifdef NVB_EXPERIMENT_NO_STORE  // timing experiment only (no results): what a step costs without the tile flush
+    if (false) {
+#else
     if (k == TS - 1) {
+#endif
       __syncwarp();
       flush_tile<REV, TS>(tPB, F, X, C0, t - k, lane);
       if (TRANS) flush_tile<REV, TS>(tPA, F, X, C0, t - k, lane);

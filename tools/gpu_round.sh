@@ -17,6 +17,6 @@ python tools/bench_show.py $out/${tag}_bench_ref.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-api --no-overlap > $out/${tag}_ncu_launches.log 2>&1
 # full capture of the DP kernels at the bench size: sweep5 plain, score, path2, sweep5 wobble, no_snp, snp3
-ncu --set full --clock-control none --import-source on -k regex:'sweep|snp3|path2|score' -c 7 -f -o $out/${tag}_full \
+ncu --set full --clock-control none --import-source on -k regex:'sweep|snp3|path2|score' -c 10 -f -o $out/${tag}_full \
   python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-api --no-overlap --no-consensus > $out/${tag}_ncu_full.log 2>&1
 echo "ncu rc=$?"
