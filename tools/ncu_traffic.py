@@ -19,5 +19,7 @@ for vals in rows[2:]:
             'dram_bytes_write': get('dram__bytes_write.sum'), 'source': os.path.basename(rep)}
     best['dram_bytes_per_launch'] = best['dram_bytes_read'] + best['dram_bytes_write']
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if best is None:
+    sys.exit('no snp3_kernel launch in ' + rep)
 json.dump(best, open(os.path.join(root, 'profiles', 'snp_traffic.json'), 'w'), indent=1)
 print(best)
