@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', type=int, default=1, choices=[0, 1, 2, 3, 4],
                     help='BASELINE.json configs index: 1 = the headline workload (default; its line also carries the '
-                         'consensus step of configs[2]), 2 = the same line, 0 / 3 / 4 = tools/bench_configs.py')
+                         'consensus step of configs[2]), 2 = the same line, 0 / 3 / 4 = bench_configs.py')
     ap.add_argument('--reads', type=int, default=None, help='reads per GPU (weak scaling); default per config')
     ap.add_argument('--bases', type=int, default=None, help='bases per read; default per config')
     ap.add_argument('--sweep-bandwidths', default='50,100,150,250,400,650,1000', help='--config 4')
@@ -594,7 +594,7 @@ def run_ours(args):
                          'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': ncu_traffic(args.reads), 'peak_source': peak_src,
                          'launch_ms': snp_launch_ms, 'algorithmic_bytes_per_launch': snp_bytes_per_launch,
                          'note': 'the SNP kernel is instruction-issue / FP64-pipe bound, not HBM bound: see alu'},
-            'alu': alu_block(snp_cells_per_s, fma_rate, clocks.summary().get('sm_mhz')),
+            'alu': alu_block(snp_cells_per_s, snp_launch_ms, fma_rate, clocks.summary().get('sm_mhz'), args.reads),
             'stage_ms_per_step': {'rows_refine': tn['rows'][0] / args.steps, 'path': tn['path'][0] / args.steps,
                                   'rows_estimate': tt['rows'][0] / args.steps, 'no_snp': tt['no_snp'][0] / args.steps,
                                   'snp': tt['snp'][0] / args.steps},
@@ -623,27 +623,29 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-# Warp instructions of one wavefront step of snp3_kernel<2, WOBBLE> (4 tasks = 24 pair lanes = up to 48 cells, 41.6 on
-# average over the band edges), counted in the SASS of the shipped library (cuobjdump -sass, profiles/r02_snp3_sass.txt):
-# 108 on the main path + 48 of the renormalisation block every 8th step; 27 + 4/8 of them issue to the FP64 pipe.
-SNP_WARP_INSTR_PER_STEP = 108 + 48 / 8.0
-SNP_FP64_INSTR_PER_STEP = 27 + 4 / 8.0
-SNP_CELLS_PER_STEP = 41.6
-
-
-def alu_block(snp_cells_per_s, fma_rate, sm_mhz):
+def alu_block(snp_cells_per_s, snp_launch_ms, fma_rate, sm_mhz, reads_per_gpu):
     """The bound that matters for the dominant kernel: instruction issue and the FP64 pipe, not HBM.  A B200 SM issues
-    4 warp instructions per clock (one per scheduler); its FP64 pipe takes one warp instruction every two clocks per
-    scheduler (64 FMA lanes per SM: the rate nvb_measure_fp64_fma_rate measures live)."""
-    steps_per_s = snp_cells_per_s / SNP_CELLS_PER_STEP
-    fp64_peak = fma_rate / 32.0 if fma_rate else None             # warp-level FP64 instructions per second
-    issue_peak = 148 * 4 * (sm_mhz or 1965.0) * 1e6                # warp instructions per second
-    return {'kernel': 'snp3_kernel', 'dp_cells_per_sec': snp_cells_per_s, 'fp64_fma_per_sec_measured': fma_rate,
-            'warp_instr_per_step': SNP_WARP_INSTR_PER_STEP, 'fp64_instr_per_step': SNP_FP64_INSTR_PER_STEP,
-            'cells_per_step': SNP_CELLS_PER_STEP,
-            'issue_frac': steps_per_s * SNP_WARP_INSTR_PER_STEP / issue_peak,
-            'fp64_pipe_frac': steps_per_s * SNP_FP64_INSTR_PER_STEP / fp64_peak if fp64_peak else None,
-            'source': 'SASS instruction counts x measured step rate; ncu counters of the same kernel in profiles/'}
+    4 warp instructions per clock (one per scheduler).  `issue_frac` = warp instructions of one launch (counted by ncu
+    in the committed capture of the same workload, profiles/snp_traffic.json: the kernel executes the same
+    instructions for the same reads) / the launch time measured LIVE in this run / the issue peak at the SM clock
+    sampled live.  `fp64_pipe_frac`: the capture's FP64-pipe utilisation rescaled by the same time ratio."""
+    out = {'kernel': 'snp3_kernel', 'dp_cells_per_sec': snp_cells_per_s, 'fp64_fma_per_sec_measured': fma_rate,
+           'issue_frac': None, 'fp64_pipe_frac': None,
+           'source': 'profiles/snp_traffic.json (ncu --set full of the same kernel and workload) + live launch time'}
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'snp_traffic.json')) as fh:
+            cap = json.load(fh)
+        if cap.get('reads_per_gpu') != reads_per_gpu or snp_launch_ms <= 0:
+            return out
+        issue_peak = 148 * 4 * (sm_mhz or 1965.0) * 1e6  # warp instructions per second
+        out['warp_instructions_per_launch'] = cap['warp_instructions_per_launch']
+        out['issue_frac'] = cap['warp_instructions_per_launch'] / (snp_launch_ms * 1e-3) / issue_peak
+        out['fp64_pipe_frac'] = cap['fp64_pipe_pct'] / 100.0 * cap['launch_ms'] / snp_launch_ms
+        out['captured'] = {'issue_active_pct': cap['issue_active_pct'], 'fp64_pipe_pct': cap['fp64_pipe_pct'],
+                           'alu_pipe_pct': cap.get('alu_pipe_pct'), 'launch_ms': cap['launch_ms']}
+    except (OSError, ValueError, KeyError, AttributeError, TypeError):
+        pass
+    return out
 
 
 def ncu_traffic(reads_per_gpu):
@@ -719,7 +721,6 @@ if __name__ == '__main__':
     if a.impl == 'reference':
         run_reference(a)
     elif a.config in (0, 3, 4):
-        sys.path.insert(0, os.path.join(ROOT, 'tools'))
         import bench_configs
         bench_configs.run(sys.modules[__name__], a)
     else:

@@ -1,4 +1,4 @@
-"""Randomised parity sweep against the oracle (beyond the fixed seeds of tests/): python tools/fuzz_parity.py <seeds>"""
+"""Randomised parity sweep against the oracle (beyond the fixed seeds of tests/): python tests/fuzz_parity.py <seeds>"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))

@@ -383,7 +383,7 @@ def test_bench_line_contract():
     assert 'workload' in line['config']
     assert line['consensus']['ranks_identical'] and line['consensus']['value'] > 0
     assert line['api']['estimate_snps']['value'] > 0 and line['api']['align_signal']['aligned'] == 24
-    assert 0 < line['alu']['issue_frac'] < 1
+    assert line['alu']['kernel'] == 'snp3_kernel' and line['alu']['dp_cells_per_sec'] > 0
     # the benchmarked reads themselves are checked against the reference inside the CPU leg
     par = line['parity']
     assert par['reads'] == 2 and par['event_mismatches'] == 0 and par['ll_mismatches'] == 0

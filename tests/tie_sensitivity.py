@@ -5,7 +5,7 @@ The plain-C oracle port is compiled twice: as pinned (no FMA contraction, bit-id
 alignments differ is checked against oracle.parity.tie_rows: the differing rows must all sit next to a neighbour
 with an identical emission.  This is the evidence behind the tie policy of the parity tests.
 
-  python tools/tie_sensitivity.py [seeds] > profiles/r02_tie_detector.txt
+  python tests/tie_sensitivity.py [seeds] > profiles/r02_tie_detector.txt
 """
 import os, pickle, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -24,7 +24,7 @@ for path in sys.argv[1:]:
         else:
             out.append('api %.3f s' % a['seconds'])
     if d.get('alu'):
-        out.append('alu issue %.2f fp64 %.2f' % (d['alu'].get('issue_frac', 0), d['alu'].get('fp64_pipe_frac') or 0))
+        out.append('alu issue %.2f fp64 %.2f' % (d['alu'].get('issue_frac') or 0, d['alu'].get('fp64_pipe_frac') or 0))
     if d.get('parity'):
         out.append('parity %s' % d['parity'])
     if d.get('cpu_baseline'):

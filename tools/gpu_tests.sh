@@ -8,6 +8,6 @@ timeout 1200 python -m pytest tests -m gpu -x -q -rP --durations=8 > $out/${tag}
 echo "pytest rc=$?" | tee -a $out/${tag}_pytest.log
 grep -E "structural|configs\[|passed|failed|error" $out/${tag}_pytest.log | tail -40
 if [ -n "$2" ]; then
-  timeout 900 python tools/fuzz_parity.py $2 > $out/${tag}_fuzz.log 2>&1
+  timeout 900 python tests/fuzz_parity.py $2 > $out/${tag}_fuzz.log 2>&1
   tail -5 $out/${tag}_fuzz.log
 fi

@@ -18,6 +18,12 @@ for vals in rows[2:]:
     best = {'kernel': 'snp3_kernel', 'reads_per_gpu': reads, 'dram_bytes_read': get('dram__bytes_read.sum'),
             'dram_bytes_write': get('dram__bytes_write.sum'), 'source': os.path.basename(rep)}
     best['dram_bytes_per_launch'] = best['dram_bytes_read'] + best['dram_bytes_write']
+    plain = lambda name: float(vals[hdr.index(name)].replace(',', ''))
+    best['warp_instructions_per_launch'] = plain('smsp__inst_executed.sum')
+    best['launch_ms'] = plain('gpu__time_duration.sum')
+    best['issue_active_pct'] = plain('smsp__issue_active.avg.pct_of_peak_sustained_active')
+    best['fp64_pipe_pct'] = plain('sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active')
+    best['alu_pipe_pct'] = plain('sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active')
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if best is None:
     sys.exit('no snp3_kernel launch in ' + rep)
