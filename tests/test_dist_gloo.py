@@ -212,12 +212,12 @@ def _exchange_worker(rank, world, port, result_dir, collective):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('collective', ['reduce_scatter', 'allreduce'])
-def test_consensus_exchange_slices_equal_single_process_gloo(tmp_path, collective):
+@pytest.mark.parametrize('collective,world', [('reduce_scatter', 2), ('allreduce', 2), ('reduce_scatter', 5)])
+def test_consensus_exchange_slices_equal_single_process_gloo(tmp_path, collective, world):
     """Reduce-scatter by genome slice + halo rows + posterior on the owned slice + all-gather == the posterior of the
-    summed chunks computed in one process (and == the all-reduce variant), on two gloo ranks."""
+    summed chunks computed in one process (and == the all-reduce variant), on two and on five gloo ranks (five: slices
+    that do not divide the rows, halos that cross group boundaries)."""
     from nadavca_b200.estimator import consensus_exchange
-    world = 2
     mp.spawn(_exchange_worker, args=(world, _free_port(), str(tmp_path), collective), nprocs=world, join=True)
     intervals, values = _make_chunks()
     want = _single_process(intervals, values)
