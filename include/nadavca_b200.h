@@ -207,6 +207,12 @@ int nvb_signal_anchors_batch(int device, const nvb_hits *hits, int32_t *anchors,
  * order statistic; a job sharded over GPUs all-reduces d_hist between the kernel and the bin choice.  Enqueues only. */
 int nvb_radix_histogram_d(int device, const double *d_values, int64_t n, int absolute_deviation, double shift,
                           uint64_t prefix, int fixed_bits, uint64_t *d_hist, void *stream);
+/* Every read normalised on its own (align_signal.py:54 calls Read.normalize_reads with one read at a time): values / out
+ * are HOST arrays, CSR over reads by off[n_reads + 1]; out = clip((values - median) / MAD, lo, hi) with the exact
+ * per-read median and MAD (one CTA per read, radix select in shared memory); shift_scale (optional, host,
+ * 2 * n_reads) receives them. */
+int nvb_normalize_each(int device, const double *values, const int64_t *off, int32_t n_reads, double lo, double hi,
+                       double *out, double *shift_scale, void *stream);
 /* d_out = clip((d_values - shift) / scale, lo, hi)  (read.py:80-81).  Enqueues only. */
 int nvb_normalize_clip_d(int device, const double *d_values, int64_t n, double shift, double scale, double lo, double hi,
                          double *d_out, void *stream);

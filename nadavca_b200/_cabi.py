@@ -97,6 +97,8 @@ SIGNATURES = {
     'nvb_radix_histogram_d': (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                                              ctypes.c_double, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p,
                                              ctypes.c_void_p]),
+    'nvb_normalize_each': (ctypes.c_int, [ctypes.c_int, c_f64p, c_i64p, ctypes.c_int32, ctypes.c_double,
+                                          ctypes.c_double, c_f64p, c_f64p, ctypes.c_void_p]),
     'nvb_normalize_clip_d': (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_double,
                                             ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_void_p,
                                             ctypes.c_void_p]),

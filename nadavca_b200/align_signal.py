@@ -103,7 +103,7 @@ def align_signal(reference_filename,
     for i, read in enumerate(reads):
         if isinstance(read, str):
             reads[i] = Read.load_from_fast5(read, group_name)
-        Read.normalize_reads([reads[i]])  # per-read median/MAD (align_signal.py:54)
+    Read.normalize_each(reads, kmer_model.device)  # per-read median / MAD (align_signal.py:54), one batch on the GPU
     results = estimator.get_refined_alignments(reads, with_event_means=True)
     for r in range(renorm_rounds):
         alive = [i for i, res in enumerate(results) if res is not None]

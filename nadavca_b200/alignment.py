@@ -204,7 +204,8 @@ def reference_codes(sequence):
         return arr.astype(numpy.int8)
     if arr.size == 0:
         return numpy.zeros(0, dtype=numpy.int8)
-    return _CODE_LUT[arr.astype('S1').view(numpy.uint8)]
+    from .genome import _as_bytes
+    return _CODE_LUT[_as_bytes(arr)]
 
 
 class ApproximateAligner:

@@ -423,14 +423,17 @@ int batch_init(nvb_batch *b, const nvb_reads *r) {
 // the pipelined stripes (rows4.cu).
 int run_sweep(nvb_batch *b, Workspace &ws, int mode, const Wave &w, cudaStream_t st) {
   const ModelDev &M = b->model->dev;
-  // Measured on B200 (profiles/r01d_sweep_schedules.txt): the rotating wavefront needs half the warp-steps but ~1.4x
-  // the instructions per step and one warp per direction instead of two.  It wins when its warps (2 per read) fill one
-  // resident wave of the GPU (16 warps per SM at its 128 registers) to 60 % or more; with fewer reads the striped
-  // sweep hides latency better, with more the second wave eats the gain.
+  // Measured on B200 (profiles/r02r_sweep_schedules.txt): the rotating wavefront needs half the warp-steps but ~1.4x the
+  // instructions per step and one warp per direction instead of two.  It wins once its warps (2 per read) fill a good
+  // part of one resident wave of the GPU (16 warps per SM at its 128 registers) -- 40 % for the plain sweep (500 reads:
+  // 13.8 against 14.1 ms), 60 % for the wobble sweep (500 reads: 21.1 against 16.5 ms, 1000 reads: 25.6 against 29.2) --
+  // and keeps winning with several waves (2000 reads: 30.2 / 45.9 ms against 39.7 / 47.3); with fewer reads the
+  // striped sweep hides latency better.
+  // (the transition sweep stores twice the rows and loses by rotating: 46 against 32 ms at 1000 reads)
   const int items = 2 * (w.b1 - w.b0);
   const int resident = b->model->sm_count * 16;
-  // (the transition sweep stores twice the rows and gains nothing from rotating: 68 against 67 ms at 1000 reads)
-  bool rotate = mode != NVB_MODE_TRANS && w.maxw <= 640 && 10 * items >= 6 * resident && items <= resident;
+  const int need_pct = mode == NVB_MODE_PLAIN ? 40 : 60;
+  bool rotate = mode != NVB_MODE_TRANS && w.maxw <= 640 && 100 * (int64_t)items >= (int64_t)need_pct * resident;
   if (g_opt.sweep != NVB_SWEEP_AUTO) rotate = w.maxw <= 640 && g_opt.sweep == NVB_SWEEP_ROTATE;
   for (int i = w.b0; i < w.b1 && rotate; i++) rotate = !b->no_rotation[i];
   if (rotate)
@@ -1008,6 +1011,31 @@ int nvb_radix_histogram_d(int device, const double *d_values, int64_t n, int abs
   nvbk_radix_hist(d_values, n, absolute_deviation ? 1 : 0, shift, (unsigned long long)prefix, fixed_bits,
                   (unsigned long long *)d_hist, (cudaStream_t)stream);
   CU(cudaGetLastError());
+  return NVB_OK;
+}
+
+int nvb_normalize_each(int device, const double *values, const int64_t *off, int32_t n_reads, double lo, double hi,
+                       double *out, double *shift_scale, void *stream) {
+  if (n_reads < 0 || !off || (n_reads > 0 && (!values || !out))) return fail(NVB_EINVAL, "bad argument");
+  if (nvb_device_count() <= device) return fail(NVB_ECUDA, "CUDA device %d not available (no CPU fallback)", device);
+  int rc = check_offsets(off, n_reads, "values");
+  if (rc) return rc;
+  for (int i = 0; i < n_reads; i++)
+    if (off[i + 1] - off[i] > 0x7fffff00LL) return fail(NVB_EINVAL, "read %d too long", i);
+  CU(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)off[n_reads];
+  DevBuf<double> d_values, d_out, d_ss;
+  DevBuf<int64_t> d_off;
+  CU(upload(d_values, values, total, st));
+  CU(upload(d_off, off, (size_t)n_reads + 1, st));
+  CU(d_out.alloc(total));
+  CU(d_ss.alloc((size_t)2 * n_reads));
+  nvbk_normalize_each(d_values.p, d_off.p, n_reads, lo, hi, d_out.p, d_ss.p, st);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, d_out.p, total * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (shift_scale) CU(cudaMemcpyAsync(shift_scale, d_ss.p, (size_t)2 * n_reads * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
   return NVB_OK;
 }
 

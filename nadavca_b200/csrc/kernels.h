@@ -61,6 +61,8 @@ void nvbk_fill_status(const BatchDev &B, int32_t *d_status, double *d_ll, int al
 // select.cu: pooled median / MAD normalisation (read.py:67-81)
 void nvbk_radix_hist(const double *d_values, int64_t n, int mode, double shift, unsigned long long prefix, int fixed,
                      unsigned long long *d_hist, cudaStream_t st);
+void nvbk_normalize_each(const double *d_values, const int64_t *d_off, int n_reads, double lo, double hi, double *d_out,
+                         double *d_shift_scale, cudaStream_t st);
 void nvbk_normalize_clip(const double *d_values, int64_t n, double shift, double scale, double lo, double hi,
                          double *d_out, cudaStream_t st);
 

@@ -79,6 +79,27 @@ class Read:
         for read in reads:
             read.normalized_signal = numpy.clip((read.raw_signal - shift) / scale, -5, 5)
 
+    @staticmethod
+    def normalize_each(reads, device):
+        """``Read.normalize_reads([read])`` for every read on its own (what align_signal does, align_signal.py:54), as
+        one batch on CUDA device `device`: exact per-read median / MAD by radix select, one CTA per read
+        (csrc/select.cu); bit-identical to the host path."""
+        import ctypes
+        from . import _cabi
+        if not reads:
+            return
+        lib = _cabi.require_device()
+        raws = [numpy.asarray(read.raw_signal, dtype=float) for read in reads]
+        off = numpy.zeros(len(reads) + 1, dtype=numpy.int64)
+        off[1:] = numpy.cumsum([len(r) for r in raws])
+        values = numpy.ascontiguousarray(numpy.concatenate(raws))
+        out = numpy.empty_like(values)
+        _cabi.check(lib.nvb_normalize_each(int(device), _cabi.ptr(values, ctypes.c_double), _cabi.ptr(off, ctypes.c_int64),
+                                           len(reads), -5.0, 5.0, _cabi.ptr(out, ctypes.c_double), None,
+                                           ctypes.c_void_p(0)), 'nvb_normalize_each')
+        for i, read in enumerate(reads):
+            read.normalized_signal = out[off[i]:off[i + 1]]
+
     def tweak_signal_normalization(self, alignment, expected_means, event_means=None):
         """Cubic smoothing spline from observed event means to expected levels (read.py:83-94).
 

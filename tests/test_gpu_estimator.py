@@ -456,6 +456,30 @@ def test_device_normalisation_equals_numpy_bit_for_bit(lib_built, n_reads):
     assert max(abs(b.normalized_signal).max() for b in gpu) == 5.0
 
 
+def test_per_read_normalisation_equals_numpy_bit_for_bit(lib_built):
+    """Read.normalize_each == Read.normalize_reads([read]) read by read (align_signal.py:54): one CTA per read, exact
+    per-read median / MAD; odd and even lengths, heavy ties, a constant-but-one read, a one-sample-over-two read."""
+    from nadavca_b200.read import Read
+    rng = np.random.default_rng(77)
+    raws = []
+    for i in range(40):
+        n = int(rng.integers(3, 6000))
+        raw = np.round(rng.normal(90, 15, size=n) * 2) / 2.0
+        if n > 20:
+            raw[rng.integers(0, n, size=4)] = rng.choice([-300.0, 800.0], size=4)
+        raws.append(raw.astype(np.int16) if i % 4 == 3 else raw)
+    raws.append(np.array([1.0, 2.0, 4.0, 8.0]))
+    raws.append(np.array([5.0, 5.0, 5.0, 9.0, 1.0]))
+    host = [Read.from_arrays(r, 'ACGT', {0: 0}) for r in raws]
+    gpu = [Read.from_arrays(r, 'ACGT', {0: 0}) for r in raws]
+    for read in host:
+        Read.normalize_reads([read])
+    Read.normalize_each(gpu, 0)
+    for a, b in zip(host, gpu):
+        assert b.normalized_signal.dtype == np.float64
+        assert np.array_equal(a.normalized_signal, b.normalized_signal)
+
+
 def test_batched_anchor_construction_matches_host_glue(lib_built):
     """csrc/anchors.cu (CIGAR walk -> matching-base anchors -> signal anchors and ranges) against the host functions
     that restate alignment.py:109-186, field by field: both strands, insertions / deletions / soft clips, mismatches,
