@@ -105,6 +105,7 @@ def align_signal(reference_filename,
             reads[i] = Read.load_from_fast5(read, group_name)
     Read.normalize_each(reads, kmer_model.device)  # per-read median / MAD (align_signal.py:54), one batch on the GPU
     results = estimator.get_refined_alignments(reads, with_event_means=True)
+    prepared = estimator.last_prepared  # the approximate alignments do not change with the normalisation
     for r in range(renorm_rounds):
         alive = [i for i, res in enumerate(results) if res is not None]
         if r % 2 == 0:
@@ -113,7 +114,8 @@ def align_signal(reference_filename,
             for i, exp in zip(alive, expected):
                 _linear_renormalization(kmer_model, reads[i], *results[i], expected=exp)
         else:
-            again = estimator.get_refined_alignments([reads[i] for i in alive], with_event_means=True)
+            again = estimator.get_refined_alignments([reads[i] for i in alive], with_event_means=True,
+                                                     prepared=[prepared[i] for i in alive])
             for i, res in zip(alive, again):
                 results[i] = res
     for read, res in zip(reads, results):

@@ -147,12 +147,18 @@ class ProbabilityEstimator:
                          workspace_limit=self.workspace_limit)
 
     # ---- path A: refined alignments ---------------------------------------------------------------------------
-    def get_refined_alignments(self, reads, with_event_means=False):
+    def get_refined_alignments(self, reads, with_event_means=False, prepared=None):
         """Batched get_refined_alignment: list (one per read) of (ApproximateSignalAlignment, int (n,3) array) or
         None for reads that are unaligned or have no valid path.  With `with_event_means` every result carries a third
         item, the mean signal level of each event (``numpy.mean(normalized_signal[start:end])`` bit for bit, computed
-        on the device) -- what the renormalisation rounds of align_signal need (align_signal.py:66-70)."""
-        prepared = [self._prepare(read) for read in reads]
+        on the device) -- what the renormalisation rounds of align_signal need (align_signal.py:66-70).
+
+        `prepared`: the value of ``self.last_prepared`` after an earlier call with the same reads -- the approximate
+        alignments (which depend on the base sequence only, not on the signal normalisation) are then reused instead
+        of asking the aligner again."""
+        if prepared is None:
+            prepared = [self._prepare(read) for read in reads]
+        self.last_prepared = prepared
         items = [it for it in prepared if it is not None]
         results = [None] * len(reads)
         if not items:
