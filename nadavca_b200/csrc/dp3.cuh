@@ -51,81 +51,129 @@ __device__ __forceinline__ double pow2neg(int e) {
   return __hiloint2double((e + 1023) << 20, 0);
 }
 
-// exp(l) = p * 2^k with p in [0.98, 1.98], any finite l (no underflow: k is returned, not applied).
-// l = (32 k + j) ln2/32 + r, |r| <= ln2/64: Cody-Waite reduction against ln2/32 (hi/lo; the hi part has 32 significant
-// bits, so n * hi is exact for |n| < 2^21), 2^(j/32) from a 32-entry table in shared memory, exp(r) - 1 by a degree-6
-// Taylor polynomial (truncation 3.5e-18; worst relative error of p measured against 60-digit arithmetic: 2.0e-16).
-// The table replaces 6 of the 13 dependent DFMAs of the single-interval polynomial this started as: the FP64 pipe
-// issues one warp instruction every two cycles, and in the latency-bound sweeps the Horner chain is on the critical path.
-#define NVB_32_LOG2E 46.16624130844683
-#define NVB_LN2_32_HI 0.02166084938653512
-#define NVB_LN2_32_LO 5.9631716539705866e-12
+// exp(l) = p * 2^k with p in [0.998, 2.0], any finite l (no underflow: k is returned, not applied).
+//
+// The argument arrives SCALED: ls = l * 256 / ln 2 (the lanes scale their emission constants once, lane_set_emission),
+// so n = rint(ls) comes from one add of the 1.5 * 2^52 constant, the remainder ls - n is exact (|ls - n| <= 1/2), and
+// l = (256 k + j) ln2/256 + r with r = (ls - n) * ln2/256, |r| <= 1.36e-3:  exp(l) = 2^k * 2^(j/256) * exp(r).
+// 2^(j/256) comes from a 256-entry table in shared memory, exp(r) - 1 from a degree-4 Taylor polynomial (truncation
+// 3.8e-17; the r^4 coefficient is 1/24 cut to its upper 32 bits, which perturbs exp(r) by 3e-18 and lets ptxas encode
+// it as an immediate).  Worst relative error of p against 60-digit arithmetic: 2.3e-16
+// (tests/test_host_logic.py::test_device_exp_restated_in_numpy reads the table and the constants out of this file).
+// History (profiles/r02q, r02w): the single-interval degree-13 polynomial of round 1 cost 13 dependent DFMAs; the
+// 32-entry table with a Cody-Waite reduction against ln2/32 cost 15 FP64 instructions per emission plus 8 integer /
+// uniform instructions that only re-materialised its constants (the SNP kernel is bound by instruction issue, and
+// ptxas prefers re-materialising to spilling under the 64-register cap); this form needs 12 FP64 and no constant
+// traffic.
+#define NVB_EXP_SCALE 369.3299304675746        // 256 / ln 2
+// ln 2 / 256, 1/24 (lower 32 bits cleared), 1/6 -- twice.  From constant memory (BANK = true) for the SNP kernel, which
+// is bound by instruction issue: ptxas hoists constant-bank LOADS into uniform registers outside its step loop, whereas
+// it re-materialises literals with two moves each inside it (-6 instructions per step).  As literals (BANK = false) for
+// the sweeps, which are bound by the latency of one warp: in their much larger loops the loads are not hoisted and a
+// constant-cache access in the dependent chain costs more than two moves (measured: wobble sweep 25.6 -> 27.8 ms).
+static __constant__ double c_exp_k[3] = {0.0027076061740622863, 0.041666656732559204, 0.16666666666666666};
+#define NVB_EXP_STEP 0.0027076061740622863
+#define NVB_EXP_C4 0.041666656732559204
+#define NVB_EXP_C3 0.16666666666666666
 
-static __constant__ double c_exp_tab[32] = {
-    1.0,                1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577,
-    1.1143867425958924, 1.1387886347566916, 1.1637248587775775, 1.189207115002721,  1.215247359980469,
-    1.241857812073484,  1.2690509571917332, 1.2968395546510096, 1.3252366431597413, 1.3542555469368927,
-    1.383909881963832,  1.4142135623730951, 1.4451808069770467, 1.4768261459394993, 1.5091644275934228,
-    1.5422108254079407, 1.5759808451078865, 1.6104903319492543, 1.645755478153965,  1.681792830507429,
-    1.718619298122478,  1.7562521603732995, 1.7947090750031072, 1.8340080864093424, 1.8741676341103,
-    1.9152065613971474, 1.9571441241754002};
-// 1/6! .. 1/3!; read as constant-bank operands of the DFMAs
-static __constant__ double c_exp_poly[4] = {1.388888888888889e-03, 8.333333333333333e-03, 4.1666666666666664e-02,
-                                            1.6666666666666666e-01};
+// 2^(j/256), correctly rounded
+static __device__ const double g_exp_tab[256] = {
+    1.0, 1.0027112750502025, 1.0054299011128027, 1.0081558981184175,
+    1.0108892860517005, 1.0136300849514894, 1.016378314910953, 1.019133996077738,
+    1.0218971486541166, 1.0246677928971357, 1.0274459491187637, 1.030231637686041,
+    1.0330248790212284, 1.0358256936019572, 1.0386341019613787, 1.041450124688316,
+    1.0442737824274138, 1.0471050958792898, 1.0499440858006872, 1.0527907730046264,
+    1.0556451783605572, 1.0585073227945128, 1.061377227289262, 1.0642549128844645,
+    1.0671404006768237, 1.0700337118202419, 1.0729348675259756, 1.075843889062791,
+    1.0787607977571199, 1.0816856149932152, 1.0846183622133092, 1.0875590609177697,
+    1.0905077326652577, 1.0934643990728858, 1.0964290818163769, 1.099401802630222,
+    1.102382583307841, 1.1053714457017412, 1.1083684117236787, 1.1113735033448175,
+    1.1143867425958924, 1.1174081515673693, 1.1204377524096067, 1.12347556733302,
+    1.1265216186082418, 1.129575928566288, 1.1326385195987192, 1.1357094141578055,
+    1.1387886347566916, 1.1418762039695616, 1.1449721444318042, 1.148076478840179,
+    1.1511892299529827, 1.154310420590216, 1.1574400736337511, 1.1605782120274988,
+    1.1637248587775775, 1.1668800369524817, 1.1700437696832502, 1.1732160801636373,
+    1.1763969916502812, 1.1795865274628758, 1.182784710984341, 1.1859915656609938,
+    1.189207115002721, 1.1924313825831512, 1.1956643920398273, 1.1989061670743806,
+    1.202156731452703, 1.2054161090051239, 1.2086843236265816, 1.2119613992768012,
+    1.215247359980469, 1.2185422298274085, 1.2218460329727576, 1.2251587936371455,
+    1.22848053610687, 1.2318112847340759, 1.2351510639369334, 1.2384998981998165,
+    1.241857812073484, 1.245224830175258, 1.2486009771892048, 1.2519862778663162,
+    1.255380757024691, 1.2587844395497165, 1.2621973503942507, 1.2656195145788063,
+    1.2690509571917332, 1.2724917033894028, 1.275941778396392, 1.2794012075056693,
+    1.2828700160787783, 1.2863482295460256, 1.2898358734066657, 1.2933329732290895,
+    1.2968395546510096, 1.3003556433796506, 1.3038812651919358, 1.3074164459346773,
+    1.3109612115247644, 1.3145155879493546, 1.318079601266064, 1.3216532776031575,
+    1.3252366431597413, 1.3288297242059544, 1.3324325470831615, 1.3360451382041458,
+    1.339667524053303, 1.3432997311868353, 1.3469417862329458, 1.3505937158920345,
+    1.3542555469368927, 1.3579273062129011, 1.3616090206382248, 1.365300717204012,
+    1.3690024229745905, 1.3727141650876684, 1.3764359707545302, 1.380167867260238,
+    1.383909881963832, 1.387662042298529, 1.3914243757719262, 1.3951969099662003,
+    1.3989796725383112, 1.4027726912202048, 1.4065759938190154, 1.4103896082172707,
+    1.4142135623730951, 1.4180478843204152, 1.4218926021691656, 1.4257477441054942,
+    1.42961333839197, 1.433489413367789, 1.4373759974489824, 1.4412731191286257,
+    1.4451808069770467, 1.449099089642035, 1.4530279958490526, 1.4569675544014438,
+    1.460917794180647, 1.4648787441464057, 1.4688504333369818, 1.4728328908693675,
+    1.4768261459394993, 1.4808302278224719, 1.4848451658727524, 1.488870989524397,
+    1.4929077282912648, 1.4969554117672355, 1.5010140696264256, 1.5050837316234065,
+    1.5091644275934228, 1.5132561874526098, 1.5173590411982147, 1.5214730189088146,
+    1.5255981507445384, 1.529734466947287, 1.533881997840956, 1.5380407738316568,
+    1.5422108254079407, 1.5463921831410214, 1.550584877685, 1.5547889397770887,
+    1.559004400237837, 1.5632312899713576, 1.567469639965553, 1.5717194812923414,
+    1.5759808451078865, 1.5802537626528246, 1.5845382652524937, 1.588834384317164,
+    1.593142151342267, 1.597461597908627, 1.6017927556826934, 1.606135656416771,
+    1.6104903319492543, 1.6148568142048607, 1.6192351351948637, 1.6236253270173289,
+    1.6280274218573478, 1.632441451987275, 1.6368674497669644, 1.6413054476440063,
+    1.645755478153965, 1.6502175739206177, 1.6546917676561943, 1.6591780921616162,
+    1.6636765803267364, 1.6681872651305825, 1.6727101796415966, 1.6772453570178785,
+    1.681792830507429, 1.6863526334483934, 1.6909247992693053, 1.6955093614893326,
+    1.7001063537185235, 1.7047158096580513, 1.709337763100463, 1.713972247929926,
+    1.718619298122478, 1.723278947746274, 1.7279512309618377, 1.732636182022311,
+    1.7373338352737062, 1.7420442251551564, 1.746767386199169, 1.7515033530318782,
+    1.7562521603732995, 1.761013843037584, 1.7657884359332727, 1.7705759740635547,
+    1.7753764925265212, 1.7801900265154245, 1.785016611318935, 1.789856282321401,
+    1.7947090750031072, 1.7995750249405351, 1.804454167806624, 1.809346539371032,
+    1.8142521755003989, 1.8191711121586085, 1.8241033854070534, 1.8290490314048973,
+    1.8340080864093424, 1.8389805867758937, 1.843966568958626, 1.8489660695104508,
+    1.8539791250833855, 1.8590057724288205, 1.864046048397789, 1.8690999899412386,
+    1.8741676341103, 1.8792490180565602, 1.8843441790323345, 1.8894531543909392,
+    1.8945759815869656, 1.8997126981765553, 1.9048633418176741, 1.9100279502703899,
+    1.9152065613971474, 1.9203992131630474, 1.925605943636125, 1.930826790987627,
+    1.9360617934922943, 1.9413109895286405, 1.9465744175792332, 1.9518521162309783,
+    1.9571441241754002, 1.9624504802089273, 1.9677712232331759, 1.9731063922552343,
+    1.978456026387951, 1.9838201648502194, 1.9891988469672663, 1.9945921121709402};
 
-static __shared__ double s_exp_tab[32];
+static __shared__ double s_exp_tab[256];
 
-// Every kernel that evaluates emissions calls this once, with ALL threads of the CTA, before anything else.
-__device__ __forceinline__ void exp_table_init() {
-  if (threadIdx.x < 32) s_exp_tab[threadIdx.x] = c_exp_tab[threadIdx.x];
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// Every kernel that evaluates emissions calls this once, with ALL threads of the CTA, before anything else; returns
+// the shared-memory address of the table (kept in a register: taking it inside the step loop costs three instructions).
+__device__ __forceinline__ unsigned exp_table_init() {
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_exp_tab[i] = g_exp_tab[i];
   __syncthreads();
+  unsigned tab = smem_u32(s_exp_tab);
+  asm volatile("" : "+r"(tab));  // opaque: otherwise the address is re-derived (S2UR + UMOV + ULEA) at every use
+  return tab;
 }
 
-#ifndef NVB_EXP_TABLE
-#define NVB_EXP_TABLE 1
-#endif
-
-#if !NVB_EXP_TABLE
-// The single-interval form (round 1): Cody-Waite against ln2 and a degree-13 Taylor polynomial on |r| <= 0.347
-// (error < 5e-18), p in [0.70, 1.42].  No table, 13 dependent DFMAs.
-#define NVB_LOG2E 1.44269504088896338700e+00
-static __constant__ double c_exp_poly13[11] = {
-    1.6059043836821613e-10, 2.08767569878681e-09,   2.505210838544172e-08,  2.755731922398589e-07,
-    2.7557319223985893e-06, 2.48015873015873e-05,   1.984126984126984e-04,  1.388888888888889e-03,
-    8.333333333333333e-03,  4.1666666666666664e-02, 1.6666666666666666e-01};
-__device__ __forceinline__ void exp_ext(double l, double &p, int &k) {
-  const double magic = 6755399441055744.0;
-  double t = fma(l, NVB_LOG2E, magic);
-  k = __double2loint(t);
-  double kd = t - magic;
-  double r = fma(-kd, NVB_LN2_HI, l);
-  r = fma(-kd, NVB_LN2_LO, r);
-  double q = c_exp_poly13[0];
-#pragma unroll
-  for (int i = 1; i < 11; i++) q = fma(q, r, c_exp_poly13[i]);
-  q = fma(q, r, 0.5);
-  q = fma(q, r, 1.0);
-  p = fma(q, r, 1.0);
-}
-#else
-__device__ __forceinline__ void exp_ext(double l, double &p, int &k) {
+template <bool BANK>
+__device__ __forceinline__ void exp_ext_scaled(double ls, unsigned tab, double &p, int &k) {
   const double magic = 6755399441055744.0;  // 1.5 * 2^52: rint via add/sub, integer in the low word
-  const double t = fma(l, NVB_32_LOG2E, magic);
+  const double t = ls + magic;
   const int n = __double2loint(t);
-  const double kd = t - magic;
-  double r = fma(-kd, NVB_LN2_32_HI, l);
-  r = fma(-kd, NVB_LN2_32_LO, r);
-  k = n >> 5;
-  const double T = s_exp_tab[n & 31];
-  double q = fma(c_exp_poly[0], r, c_exp_poly[1]);
-  q = fma(q, r, c_exp_poly[2]);
-  q = fma(q, r, c_exp_poly[3]);
+  const double r = (ls - (t - magic)) * (BANK ? c_exp_k[0] : NVB_EXP_STEP);
+  k = n >> 8;
+  double T;
+  // (bank conflicts of the 256-entry lookup do not show: a timing build that folded the index to 32 entries ran the
+  // sweeps and the SNP kernel in the same time, profiles/r02w)
+  asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(tab + ((unsigned)(n & 255) << 3)));
+  double q = BANK ? fma(r, c_exp_k[1], c_exp_k[2]) : fma(r, NVB_EXP_C4, NVB_EXP_C3);
   q = fma(q, r, 0.5);
   q = fma(q, r, 1.0);
   q *= r;             // exp(r) - 1
   p = fma(T, q, T);
 }
-#endif
 
 // natural log of f * 2^E (f > 0), E*ln2 added in two pieces
 __device__ __forceinline__ double log_ext(double f, int E) {
@@ -194,7 +242,6 @@ struct SignalRing {
   int off;       // index of the read's sample 0 relative to RingState::base (0..255)
 };
 
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 template <int NS>
 __device__ __forceinline__ RingState *ring_state(const SignalRing<NS> &R) {
   return reinterpret_cast<RingState *>(__cvta_shared_to_generic(R.buf + NS * 256 + NS * 8));
@@ -344,7 +391,8 @@ struct LaneCfg {
   int ws, we;        // A-row band (INT_MIN..INT_MAX for lanes without an A-row: their A-row is P itself).  Both ends
                      // are needed: the far end of the band is `we` in a forward sweep and `ws` in a reverse sweep
   int ms, me;        // B-row band; LOADER: band of the row it loads; JOIN: band of the closing suffix row
-  double mu, ac, mc; // own Gaussian emission (PAIR: model row; LOADER: the row before the first pair; JOIN: last+1)
+  double mu, ac, mc; // own Gaussian emission (PAIR: model row; LOADER: the row before the first pair; JOIN: last+1);
+                     // ac and mc are SCALED by 256 / ln 2 (lane_set_emission), see exp_ext_scaled
   double cm;         // A-row mixture weight: exp(-2) (kmer_model.cpp:60), 0 for lanes without an A-row
   int abias;         // 0, or NVB_EZERO for lanes without an A-row (their mixture term must stay zero-class)
   double pc;         // transition rows: constant emission 0.01 = 0.64 * 2^-6, or 0 (kmer_model.cpp:64-94)
@@ -354,6 +402,11 @@ struct LaneCfg {
 __device__ __forceinline__ void lane_cfg_clear(LaneCfg &L) {
   L.role = NVB_ROLE_IDLE; L.ws = -0x7fffffff - 1; L.we = 0x7fffffff; L.ms = 0x7fffffff; L.me = 0;  // empty B band
   L.mu = 0; L.ac = 0; L.mc = 0; L.cm = 0; L.abias = NVB_EZERO; L.pc = 0; L.kc = NVB_EZERO;
+}
+
+// Gaussian emission of a lane from the model tables: log density ac - (x - mu)^2 * mc (kmer_model.cpp:47-51).
+__device__ __forceinline__ void lane_set_emission(LaneCfg &L, double mu, double ac, double mc) {
+  L.mu = mu; L.ac = ac * NVB_EXP_SCALE; L.mc = mc * NVB_EXP_SCALE;
 }
 
 template <int MEL>
@@ -392,15 +445,15 @@ struct LaneOut {
 // it off); lanes without an output use ms = INT_MAX.  Measured neutral on the SNP kernel, so currently unused.
 // The step comes in two halves so that the latency-bound sweeps can evaluate the emission of step t+1 (which depends
 // on nothing but the sample) while the state update of step t waits for its neighbour: lane_emit + lane_update.
-__device__ __forceinline__ void lane_emit(const LaneCfg &L, double x, double &p, int &kk) {
+template <bool BANK = false>
+__device__ __forceinline__ void lane_emit(const LaneCfg &L, unsigned tab, double x, double &p, int &kk) {
 #ifdef NVB_EXPERIMENT_NO_EMIT  // timing experiment only (wrong results): what a step costs without its emission
   p = 1.0 + 1e-9 * x; kk = 0;
   return;
 #endif
-  // own emission, reference formula ac - d*d*mc (kmer_model.cpp:47-51)
+  // own emission, reference formula ac - d*d*mc (kmer_model.cpp:47-51), in units of ln2/256
   const double d = x - L.mu;
-  const double l = L.ac - d * d * L.mc;
-  exp_ext(l, p, kk);
+  exp_ext_scaled<BANK>(fma(-(d * d), L.mc, L.ac), tab, p, kk);
 }
 
 template <int MEL, int MODE, bool WITH_JOIN, int PH, bool FWD_ONLY>
@@ -408,11 +461,11 @@ __device__ __forceinline__ void lane_update(const LaneCfg &L, LaneState<MEL> &S,
                                             const LaneOut &in, double sF, int sX, LaneOut &out, XD &aout);
 
 template <int MEL, int MODE, bool WITH_JOIN, int PH, bool FWD_ONLY>
-__device__ __forceinline__ void lane_step(const LaneCfg &L, LaneState<MEL> &S, int c, double x, const LaneOut &in,
-                                          double sF, int sX, LaneOut &out, XD &aout) {
+__device__ __forceinline__ void lane_step(const LaneCfg &L, LaneState<MEL> &S, unsigned tab, int c, double x,
+                                          const LaneOut &in, double sF, int sX, LaneOut &out, XD &aout) {
   double p;
   int kk;
-  lane_emit(L, x, p, kk);
+  lane_emit<true>(L, tab, x, p, kk);  // lane_step is the SNP kernel's form
   lane_update<MEL, MODE, WITH_JOIN, PH, FWD_ONLY>(L, S, c, p, kk, in, sF, sX, out, aout);
 }
 

@@ -103,7 +103,8 @@ struct Handoff {
 
 template <int MEL, int MODE, bool REV>
 __device__ __forceinline__ void sweep_stripes(const ModelDev &M, const ReadView &v, double *F, int32_t *X, int lane, int warp, int NW,
-                              const Handoff &H, const StoreTile &tileB, const StoreTile &tileA, const SignalRing<4> &R) {
+                              const Handoff &H, const StoreTile &tileB, const StoreTile &tileA, const SignalRing<4> &R,
+                              unsigned exp_tab) {
   constexpr int mode = MODE;
   const int n = v.n, N = v.N;
   const double C_E2 = 0.1353352832366127;  // exp(-2): the "/ 2" of kmer_model.cpp:60 is "- 2.0" in log space
@@ -145,12 +146,12 @@ __device__ __forceinline__ void sweep_stripes(const ModelDev &M, const ReadView 
       const PairGeom pg = pair_geom<REV>(v, mode, g0);
       const int nb = (g0 > 0) ? pg.nb : pg.base;  // emission of the model row before the stripe
       const int id = kmer_id(M, v, nb, INT32_MIN, 0);
-      L.mu = M.mean[id]; L.ac = M.ac[id]; L.mc = M.mc[id];
+      lane_set_emission(L, M.mean[id], M.ac[id], M.mc[id]);
     } else if (lane <= npairs) {
       const PairGeom pg = pair_geom<REV>(v, mode, g0 + lane - 1);
       const int id = kmer_id(M, v, pg.base, INT32_MIN, 0);
       L.role = NVB_ROLE_PAIR;
-      L.mu = M.mean[id]; L.ac = M.ac[id]; L.mc = M.mc[id];
+      lane_set_emission(L, M.mean[id], M.ac[id], M.mc[id]);
       ws = v.bs[pg.aband]; awe = v.be[pg.aband];
       L.ms = v.bs[pg.bband]; L.me = v.be[pg.bband];
       aoff = pg.aoff; boff = pg.boff; storeA = pg.storeA && pg.hasA; storeB = 1;
@@ -200,7 +201,7 @@ __device__ __forceinline__ void sweep_stripes(const ModelDev &M, const ReadView 
     stage(0);
     double p_cur;
     int k_cur;
-    lane_emit(L, ring_read(R, sample_index(0)), p_cur, k_cur);  // emissions are evaluated one step ahead
+    lane_emit(L, exp_tab, ring_read(R, sample_index(0)), p_cur, k_cur);  // emissions are evaluated one step ahead
     unsigned ready = 0;  // cells of the hand-off row known to be ready (sweep order)
     const unsigned row_cells = (unsigned)(le - ls + 1);
     for (int t = 0; t < T; t++) {
@@ -224,7 +225,7 @@ __device__ __forceinline__ void sweep_stripes(const ModelDev &M, const ReadView 
       // neighbour's shuffle
       const double p = p_cur;
       const int kk = k_cur;
-      lane_emit(L, ring_read(R, sample_index(t + 1)), p_cur, k_cur);
+      lane_emit(L, exp_tab, ring_read(R, sample_index(t + 1)), p_cur, k_cur);
       LaneOut in = shfl_up_out<MODE>(out);
       XD aout;
       lane_update<MEL, MODE, false, -1, false>(L, S, c, p, kk, in, 1.0, 0, out, aout);
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(224, 4) sweep4_kernel(ModelDev M, BatchDev B, 
   extern __shared__ unsigned long long smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x;  // (read, direction)
-  exp_table_init();
+  const unsigned exp_tab = exp_table_init();
   if (item >= n_items) return;
   const int b = b0 + (item >> 1);
   if (B.flags[b]) return;
@@ -319,8 +320,8 @@ __global__ void __launch_bounds__(224, 4) sweep4_kernel(ModelDev M, BatchDev B, 
   __syncthreads();
   ReadView v = read_view(B, b);
   const int64_t base = mat_base[b];
-  if (item & 1) sweep_stripes<MEL, MODE, true>(M, v, sF + base, sX + base, lane, warp, NW, H, tileB, tileA, R);
-  else sweep_stripes<MEL, MODE, false>(M, v, pF + base, pX + base, lane, warp, NW, H, tileB, tileA, R);
+  if (item & 1) sweep_stripes<MEL, MODE, true>(M, v, sF + base, sX + base, lane, warp, NW, H, tileB, tileA, R, exp_tab);
+  else sweep_stripes<MEL, MODE, false>(M, v, pF + base, pX + base, lane, warp, NW, H, tileB, tileA, R, exp_tab);
 }
 
 // Node::TotalLikelihood(prefix[n], suffix[n]) (dtw.cpp:83-85); suffix[n] is all ones.  Two passes over the row:

@@ -24,15 +24,17 @@ namespace {
 #endif
 
 // Steps per store tile; pairs are (de)activated only at multiples of it.  The per-tile work (slot management, ring
-// upkeep, the transposing flush: ~300 warp instructions) is amortised over the tile, but a coarser tile keeps pairs in
-// their slots longer, so the second slot -- which makes the whole warp run the step body twice -- is live more often.
-// Measured at 1000 reads (profiles/r02e): 8 steps win for the plain sweep (18.4 -> 16.6 ms), 4 for the wobble sweep
-// (25.6 against 26.7 ms).  8 is the largest value the slot-reuse guarantee of band.cu (be[j] - bs[j+63] <= 48) allows.
+// upkeep, the transposing flush: ~300 warp instructions) is amortised over the tile; a coarser tile keeps pairs in
+// their slots longer, so the second slot -- which makes the whole warp run the step body twice -- is live a little
+// more often (3.6 % of the 8-step tiles against 2.4 % of the 4-step tiles on the bench reads).  Measured at 1000 reads:
+// 8 steps win for the plain sweep (18.4 -> 16.6 ms, profiles/r02e) and, since the round-2 emission code, for the wobble
+// sweep too (25.3 against 26.9 ms, profiles/r02w; with the round-1 emission 4 steps were better, 25.6 against 26.7).
+// 8 is the largest value the slot-reuse guarantee of band.cu (be[j] - bs[j+63] <= 48) allows.
 #ifndef NVB_ROT_TS_PLAIN
 #define NVB_ROT_TS_PLAIN 8
 #endif
 #ifndef NVB_ROT_TS_OTHER
-#define NVB_ROT_TS_OTHER 4
+#define NVB_ROT_TS_OTHER 8
 #endif
 __host__ __device__ constexpr int tile_steps(int mode) { return mode == NVB_MODE_PLAIN ? NVB_ROT_TS_PLAIN : NVB_ROT_TS_OTHER; }
 
@@ -122,7 +124,7 @@ __device__ __forceinline__ int sample_index(const ReadView &v, int C0, int g, in
 
 template <int MEL, int MODE, bool REV>
 __device__ __forceinline__ void slot_start(Slot<MEL> &Q, const ModelDev &M, const ReadView &v, const SignalRing<8> &R,
-                                           int C0, int g, int t) {
+                                           unsigned exp_tab, int C0, int g, int t) {
   const int n = v.n;
   const int i = pair_base<REV>(n, g);
   const double C_E2 = 0.1353352832366127;  // exp(-2): the "/ 2" of kmer_model.cpp:60 is "- 2.0" in log space
@@ -133,7 +135,7 @@ __device__ __forceinline__ void slot_start(Slot<MEL> &Q, const ModelDev &M, cons
   const int aband = REV ? i + 1 : i, bband = REV ? i : i + 1, nb = REV ? i + 1 : i - 1;
   const int id = kmer_id(M, v, i, INT32_MIN, 0);
   Q.L.role = NVB_ROLE_PAIR;
-  Q.L.mu = M.mean[id]; Q.L.ac = M.ac[id]; Q.L.mc = M.mc[id];
+  lane_set_emission(Q.L, M.mean[id], M.ac[id], M.mc[id]);
   Q.L.ms = v.bs[bband]; Q.L.me = v.be[bband];
   if (MODE == NVB_MODE_TRANS) {
     Q.aoff = trans_row_off(v, REV ? 2 * i + 1 : 2 * i);
@@ -153,12 +155,13 @@ __device__ __forceinline__ void slot_start(Slot<MEL> &Q, const ModelDev &M, cons
       Q.L.cm = C_E2; Q.L.abias = 0;
     }
   }
-  lane_emit(Q.L, ring_read(R, sample_index<REV>(v, C0, g, t)), Q.p_cur, Q.k_cur);  // emission of its first step
+  lane_emit(Q.L, exp_tab, ring_read(R, sample_index<REV>(v, C0, g, t)), Q.p_cur, Q.k_cur);  // emission of its first step
 }
 
 // One step of one slot.  `pf .. pk, ptag` = outputs of the producer lane's slot(s) at the previous step.
 template <int MEL, int MODE, bool REV>
-__device__ __forceinline__ void slot_step(Slot<MEL> &Q, const ReadView &v, const SignalRing<8> &R, int C0, int t,
+__device__ __forceinline__ void slot_step(Slot<MEL> &Q, const ReadView &v, const SignalRing<8> &R, unsigned exp_tab,
+                                          int C0, int t,
                                           const LaneOut &in0, int tag0, const LaneOut &in1, int tag1, bool have1,
                                           int ones_s, int ones_e) {
   const int g = Q.pair;
@@ -167,7 +170,7 @@ __device__ __forceinline__ void slot_step(Slot<MEL> &Q, const ReadView &v, const
   // independently of the state update of step t below, so that the two dependency chains overlap
   const double p = Q.p_cur;
   const int kk = Q.k_cur;
-  lane_emit(Q.L, ring_read(R, sample_index<REV>(v, C0, g, t + 1)), Q.p_cur, Q.k_cur);
+  lane_emit(Q.L, exp_tab, ring_read(R, sample_index<REV>(v, C0, g, t + 1)), Q.p_cur, Q.k_cur);
   LaneOut in;
   const int want = g - 1;
   if (g == 0) {  // the all-ones initial row (dtw.cpp:50,66,182,190)
@@ -212,7 +215,7 @@ __device__ __forceinline__ void write_meta(const StoreTile &tb, const StoreTile 
 
 template <int MEL, int MODE, bool REV>
 __device__ void sweep_rotate(const ModelDev &M, const ReadView &v, double *F, int32_t *X, int lane,
-                             const StoreTile (&tiles)[4], const SignalRing<8> &R) {
+                             const StoreTile (&tiles)[4], const SignalRing<8> &R, unsigned exp_tab) {
   const int n = v.n;
   constexpr bool TRANS = (MODE == NVB_MODE_TRANS);
   constexpr int TS = tile_steps(MODE), TSTRIDE = TS + 1;
@@ -263,8 +266,8 @@ __device__ void sweep_rotate(const ModelDev &M, const ReadView &v, double *F, in
         }
       }
       if (starting) {
-        if (P.pair < 0) slot_start<MEL, MODE, REV>(P, M, v, R, C0, next_g, t);
-        else slot_start<MEL, MODE, REV>(Q2, M, v, R, C0, next_g, t);  // the band kernel guarantees Q2 is free
+        if (P.pair < 0) slot_start<MEL, MODE, REV>(P, M, v, R, exp_tab, C0, next_g, t);
+        else slot_start<MEL, MODE, REV>(Q2, M, v, R, exp_tab, C0, next_g, t);  // the band kernel guarantees Q2 is free
         next_g += NVB_WARP;
         next_start = (next_g < n) ? pair_t_start<REV>(v, C0, next_g) : 0x7fffffff;
       }
@@ -286,12 +289,12 @@ __device__ void sweep_rotate(const ModelDev &M, const ReadView &v, double *F, in
     }
     // ---- the step(s) ------------------------------------------------------------------------------------------------
     const int k = t & (TS - 1);
-    if (P.pair >= 0) slot_step<MEL, MODE, REV>(P, v, R, C0, t, in0, tag0, in1, tag1, any2_tile, ones_s, ones_e);
+    if (P.pair >= 0) slot_step<MEL, MODE, REV>(P, v, R, exp_tab, C0, t, in0, tag0, in1, tag1, any2_tile, ones_s, ones_e);
     tPB.f[lane * TSTRIDE + k] = P.out.f;
     tPB.x[lane * TSTRIDE + k] = P.out.E;
     if (TRANS) { tPA.f[lane * TSTRIDE + k] = P.aout.f; tPA.x[lane * TSTRIDE + k] = P.aout.e; }
     if (any2_tile) {
-      if (Q2.pair >= 0) slot_step<MEL, MODE, REV>(Q2, v, R, C0, t, in0, tag0, in1, tag1, true, ones_s, ones_e);
+      if (Q2.pair >= 0) slot_step<MEL, MODE, REV>(Q2, v, R, exp_tab, C0, t, in0, tag0, in1, tag1, true, ones_s, ones_e);
       tSB.f[lane * TSTRIDE + k] = Q2.out.f;
       tSB.x[lane * TSTRIDE + k] = Q2.out.E;
       if (TRANS) { tSA.f[lane * TSTRIDE + k] = Q2.aout.f; tSA.x[lane * TSTRIDE + k] = Q2.aout.e; }
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(64, NVB_ROT_MIN_BLOCKS) sweep5_kernel(ModelDev
   extern __shared__ unsigned long long smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * (blockDim.x >> 5) + warp;  // (read, direction)
-  exp_table_init();
+  const unsigned exp_tab = exp_table_init();
   if (item >= n_items) return;
   const int b = b0 + (item >> 1);
   if (B.flags[b] != 0) return;  // bad band
@@ -343,8 +346,8 @@ __global__ void __launch_bounds__(64, NVB_ROT_MIN_BLOCKS) sweep5_kernel(ModelDev
   // signal ring (dp3.cuh) behind the four store tiles: 8 chunks of 32 samples + 8 mbarriers, filled by TMA bulk copies
   SignalRing<8> R;
   ring_init(R, base + tiles_per_warp(MODE) * tile_bytes(tile_steps(MODE)), B.signal, B.sig_off[b], B.sig_off[B.n_reads], lane);
-  if (item & 1) sweep_rotate<MEL, MODE, true>(M, v, sF + mb, sX + mb, lane, tiles, R);
-  else sweep_rotate<MEL, MODE, false>(M, v, pF + mb, pX + mb, lane, tiles, R);
+  if (item & 1) sweep_rotate<MEL, MODE, true>(M, v, sF + mb, sX + mb, lane, tiles, R, exp_tab);
+  else sweep_rotate<MEL, MODE, false>(M, v, pF + mb, pX + mb, lane, tiles, R, exp_tab);
 }
 
 template <int MEL, int MODE>

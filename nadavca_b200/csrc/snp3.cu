@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(128) snp3_kernel(ModelDev M, BatchDev B, int b
                                                    const int32_t *pX, const double *sF, const int32_t *sX,
                                                    double *out_ll) {
   constexpr bool wobbling = (MODE == NVB_MODE_WOBBLE);
-  exp_table_init();
+  const unsigned exp_tab = exp_table_init();
   const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t warp_id = blockIdx.x * (int64_t)(blockDim.x >> 5) + wic;
   const int A = M.alphabet;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(128) snp3_kernel(ModelDev M, BatchDev B, int b
       if (hasA) { L.cm = C_E2; L.abias = 0; }
       if (kmer_at >= 0) {
         const int id = kmer_id(M, v, kmer_at, i, base);  // ModifiedSequence (sequence.cpp:30-38)
-        L.mu = M.mean[id]; L.ac = M.ac[id]; L.mc = M.mc[id];
+        lane_set_emission(L, M.mean[id], M.ac[id], M.mc[id]);
       }
     }
   }
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(128) snp3_kernel(ModelDev M, BatchDev B, int b
     }
     XD aout;
     // JOIN lanes multiply their A-row cell by the closing suffix cell, every other lane by (1.0, 0)
-    lane_step<MEL, MODE, true, -1, false>(L, S, c, x, in, is_join ? rF : 1.0, is_join ? rX : 0, res, aout);
+    lane_step<MEL, MODE, true, -1, false>(L, S, exp_tab, c, x, in, is_join ? rF : 1.0, is_join ? rX : 0, res, aout);
     if (is_loader) {  // the loader's output is the stored prefix row (zero outside its band)
       res.f = rF; res.E = rX;
     } else if (!passes) {

@@ -332,3 +332,44 @@ def test_fit_splines_pool_equals_inline(golden_estimator):
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
     for a, b in zip(inline, few):
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_device_exp_restated_in_numpy():
+    """The emission exp of csrc/dp3.cuh (exp_ext_scaled: scaled argument, 256-entry table, degree-4 polynomial),
+    restated with the table and the constants READ FROM THE SOURCE, against 60-digit arithmetic: every table entry is
+    the correctly rounded 2^(j/256) and p * 2^k is within 3e-16 of exp over the whole range of emission exponents."""
+    import re
+    import mpmath
+    mpmath.mp.prec = 200
+    src = open(os.path.join(ROOT, 'nadavca_b200', 'csrc', 'dp3.cuh')).read()
+    body = src[src.index('g_exp_tab[256] = {') + len('g_exp_tab[256] = {'):]
+    tab = np.array([float(x) for x in body[:body.index('};')].replace('\n', ' ').split(',')])
+    assert len(tab) == 256
+    for j in range(256):
+        assert tab[j] == float(mpmath.power(2, mpmath.mpf(j) / 256))
+    step, c4, c3 = [float(x) for x in re.search(r'c_exp_k\[3\] = \{([^}]*)\}', src).group(1).split(',')]
+    scale = float(re.search(r'#define NVB_EXP_SCALE ([0-9.]+)', src).group(1))
+    assert scale == float(256 / mpmath.log(2)) and step == float(mpmath.log(2) / 256)
+    assert np.float64(c4).view(np.uint64) & np.uint64(0xffffffff) == 0 and abs(c4 * 24 - 1) < 2e-6
+
+    def fma(a, b, c):
+        return float(mpmath.mpf(a) * mpmath.mpf(b) + mpmath.mpf(c))
+
+    rng = np.random.default_rng(0)
+    logs = np.concatenate([rng.uniform(-60, 3, 1500), rng.uniform(-3300, -60, 400), -np.abs(rng.normal(0, 1e-3, 100)),
+                           [0.0, -1e-300, 2.5]])
+    magic = 6755399441055744.0
+    worst = 0.0
+    for ls in logs * scale:
+        t = ls + magic
+        n = int(t - magic)
+        r = (ls - (t - magic)) * step
+        q = fma(r, c4, c3)
+        q = fma(q, r, 0.5)
+        q = fma(q, r, 1.0)
+        q = q * r
+        p = fma(tab[n & 255], q, tab[n & 255])
+        assert 0.99 < p < 2.0
+        true = mpmath.exp(mpmath.mpf(ls) * mpmath.log(2) / 256)
+        worst = max(worst, abs(float((mpmath.mpf(p) * mpmath.power(2, n >> 8) - true) / true)))
+    assert worst < 3e-16, worst
