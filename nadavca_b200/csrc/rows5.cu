@@ -164,25 +164,30 @@ __device__ __forceinline__ void slot_step(Slot<MEL> &Q, const ReadView &v, const
                                           int C0, int t,
                                           const LaneOut &in0, int tag0, const LaneOut &in1, int tag1, bool have1,
                                           int ones_s, int ones_e) {
+  // Runs for EVERY lane, also those whose slot is free (pair -1: cleared configuration, empty bands, zero state, so
+  // the step computes zeros that nobody reads): a per-lane `if (pair >= 0)` around ~150 instructions costs a
+  // BSSY / BRA / BSYNC triple and a reconvergence stall at every step (ncu r02o: 13 % of the stall samples of the
+  // sweep sat on control-flow instructions).  For the same reason the inflow is chosen by selects, not branches.
   const int g = Q.pair;
+  const bool live = g >= 0;
   const int c = REV ? C0 - (t - g) : C0 + (t - g);
   // the emission of step t+1 depends on nothing but its sample (staged in shared memory): it is evaluated here,
   // independently of the state update of step t below, so that the two dependency chains overlap
   const double p = Q.p_cur;
   const int kk = Q.k_cur;
-  lane_emit(Q.L, exp_tab, ring_read(R, sample_index<REV>(v, C0, g, t + 1)), Q.p_cur, Q.k_cur);
-  LaneOut in;
+  // (a free slot would read a sample outside the staged window: give it a harmless one)
+  const double x_next = ring_read(R, sample_index<REV>(v, C0, g, t + 1));
+  lane_emit(Q.L, exp_tab, live ? x_next : 0.0, Q.p_cur, Q.k_cur);
   const int want = g - 1;
-  if (g == 0) {  // the all-ones initial row (dtw.cpp:50,66,182,190)
-    const bool inb = c >= ones_s && c <= ones_e;
-    in.f = inb ? 1.0 : 0.0; in.E = inb ? 0 : NVB_EZERO; in.p = 1.0; in.k = 0;
-  } else if (tag0 == want) {
-    in = in0;
-  } else if (have1 && tag1 == want) {
-    in = in1;
-  } else {  // the producer has left its band: nothing flows any more
-    in.f = 0.0; in.E = NVB_EZERO; in.p = 1.0; in.k = 0;
-  }
+  const bool first = g == 0;                               // the all-ones initial row (dtw.cpp:50,66,182,190)
+  const bool ones = first && c >= ones_s && c <= ones_e;
+  const bool m0 = live && !first && tag0 == want;
+  const bool m1 = live && !first && !m0 && have1 && tag1 == want;
+  LaneOut in;  // neither: the producer has left its band, nothing flows any more
+  in.f = ones ? 1.0 : (m0 ? in0.f : (m1 ? in1.f : 0.0));
+  in.E = ones ? 0 : (m0 ? in0.E : (m1 ? in1.E : NVB_EZERO));
+  in.p = m0 ? in0.p : (m1 ? in1.p : 1.0);
+  in.k = m0 ? in0.k : (m1 ? in1.k : 0);
   lane_update<MEL, MODE, false, -1, false>(Q.L, Q.S, c, p, kk, in, 1.0, 0, Q.out, Q.aout);
 }
 
@@ -289,12 +294,12 @@ __device__ void sweep_rotate(const ModelDev &M, const ReadView &v, double *F, in
     }
     // ---- the step(s) ------------------------------------------------------------------------------------------------
     const int k = t & (TS - 1);
-    if (P.pair >= 0) slot_step<MEL, MODE, REV>(P, v, R, exp_tab, C0, t, in0, tag0, in1, tag1, any2_tile, ones_s, ones_e);
+    slot_step<MEL, MODE, REV>(P, v, R, exp_tab, C0, t, in0, tag0, in1, tag1, any2_tile, ones_s, ones_e);
     tPB.f[lane * TSTRIDE + k] = P.out.f;
     tPB.x[lane * TSTRIDE + k] = P.out.E;
     if (TRANS) { tPA.f[lane * TSTRIDE + k] = P.aout.f; tPA.x[lane * TSTRIDE + k] = P.aout.e; }
     if (any2_tile) {
-      if (Q2.pair >= 0) slot_step<MEL, MODE, REV>(Q2, v, R, exp_tab, C0, t, in0, tag0, in1, tag1, true, ones_s, ones_e);
+      slot_step<MEL, MODE, REV>(Q2, v, R, exp_tab, C0, t, in0, tag0, in1, tag1, true, ones_s, ones_e);
       tSB.f[lane * TSTRIDE + k] = Q2.out.f;
       tSB.x[lane * TSTRIDE + k] = Q2.out.E;
       if (TRANS) { tSA.f[lane * TSTRIDE + k] = Q2.aout.f; tSA.x[lane * TSTRIDE + k] = Q2.aout.e; }
