@@ -244,8 +244,13 @@ __device__ void sweep_rotate(const ModelDev &M, const ReadView &v, double *F, in
   int next_start = (next_g < n) ? pair_t_start<REV>(v, C0, next_g) : 0x7fffffff;
   bool any2_tile = false;                              // some lane had a live second slot during this tile
 
-  for (int t = 0; t < T_total; t++) {
-    if ((t & (TS - 1)) == 0) {
+  // One iteration per store tile: slot management, then TS steps (two copies of the step loop, with and without the
+  // second slot, so that the steps themselves carry no tile / flush / renormalisation / second-slot tests), then the
+  // flush.
+  static_assert(((NVB_RENORM_MASK + 1) % TS) == 0 || (TS % (NVB_RENORM_MASK + 1)) == 0, "tile vs renormalisation period");
+  const int src = (lane + NVB_WARP - 1) & (NVB_WARP - 1);
+  for (int t = 0; t < T_total; t += TS) {
+    {
       // ---- slot management, only at tile boundaries -----------------------------------------------------------
       // a pair keeps its slot until the step AFTER its last in-band one: that is when its last cell is consumed
       if (P.pair >= 0 && t >= P.t_end + 2) {
@@ -281,44 +286,54 @@ __device__ void sweep_rotate(const ModelDev &M, const ReadView &v, double *F, in
       if (any2_tile) write_meta(tSB, tSA, Q2, lane, TRANS);
       __syncwarp();
     }
-    // ---- neighbour outputs of the previous step: rotation by one lane, tagged with the pair index -----------------
-    const int src = (lane + NVB_WARP - 1) & (NVB_WARP - 1);
-    const LaneOut in0 = rotate_out<MODE>(P.out, src);
-    const int tag0 = __shfl_sync(NVB_FULL, P.pair, src);
-    LaneOut in1;
-    in1.f = 0.0; in1.E = NVB_EZERO; in1.p = 1.0; in1.k = 0;
-    int tag1 = -1;
-    if (any2_tile) {
-      in1 = rotate_out<MODE>(Q2.out, src);
-      tag1 = __shfl_sync(NVB_FULL, Q2.pair, src);
-    }
-    // ---- the step(s) ------------------------------------------------------------------------------------------------
-    const int k = t & (TS - 1);
-    slot_step<MEL, MODE, REV>(P, v, R, exp_tab, C0, t, in0, tag0, in1, tag1, any2_tile, ones_s, ones_e);
-    tPB.f[lane * TSTRIDE + k] = P.out.f;
-    tPB.x[lane * TSTRIDE + k] = P.out.E;
-    if (TRANS) { tPA.f[lane * TSTRIDE + k] = P.aout.f; tPA.x[lane * TSTRIDE + k] = P.aout.e; }
-    if (any2_tile) {
-      slot_step<MEL, MODE, REV>(Q2, v, R, exp_tab, C0, t, in0, tag0, in1, tag1, true, ones_s, ones_e);
-      tSB.f[lane * TSTRIDE + k] = Q2.out.f;
-      tSB.x[lane * TSTRIDE + k] = Q2.out.E;
-      if (TRANS) { tSA.f[lane * TSTRIDE + k] = Q2.aout.f; tSA.x[lane * TSTRIDE + k] = Q2.aout.e; }
-    }
-#ifdef NVB_EXPERIMENT_NO_STORE  // timing experiment only (no results): what a step costs without the tile flush
-    if (false) {
-#else
-    if (k == TS - 1) {
-#endif
-      __syncwarp();
-      flush_tile<REV, TS>(tPB, F, X, C0, t - k, lane);
-      if (TRANS) flush_tile<REV, TS>(tPA, F, X, C0, t - k, lane);
-      if (any2_tile) {
-        flush_tile<REV, TS>(tSB, F, X, C0, t - k, lane);
-        if (TRANS) flush_tile<REV, TS>(tSA, F, X, C0, t - k, lane);
+    if (!any2_tile) {
+#pragma unroll 1
+      for (int k = 0; k < TS; k++) {
+        // neighbour outputs of the previous step: rotation by one lane, tagged with the pair index
+        const LaneOut in0 = rotate_out<MODE>(P.out, src);
+        const int tag0 = __shfl_sync(NVB_FULL, P.pair, src);
+        LaneOut none;
+        none.f = 0.0; none.E = NVB_EZERO; none.p = 1.0; none.k = 0;
+        slot_step<MEL, MODE, REV>(P, v, R, exp_tab, C0, t + k, in0, tag0, none, -1, false, ones_s, ones_e);
+        tPB.f[lane * TSTRIDE + k] = P.out.f;
+        tPB.x[lane * TSTRIDE + k] = P.out.E;
+        if (TRANS) { tPA.f[lane * TSTRIDE + k] = P.aout.f; tPA.x[lane * TSTRIDE + k] = P.aout.e; }
+        if (((t + k) & NVB_RENORM_MASK) == NVB_RENORM_MASK && TS > NVB_RENORM_MASK + 1) lane_renorm(P.S);
       }
-      __syncwarp();
+    } else {
+#pragma unroll 1
+      for (int k = 0; k < TS; k++) {
+        const LaneOut in0 = rotate_out<MODE>(P.out, src);
+        const int tag0 = __shfl_sync(NVB_FULL, P.pair, src);
+        const LaneOut in1 = rotate_out<MODE>(Q2.out, src);
+        const int tag1 = __shfl_sync(NVB_FULL, Q2.pair, src);
+        slot_step<MEL, MODE, REV>(P, v, R, exp_tab, C0, t + k, in0, tag0, in1, tag1, true, ones_s, ones_e);
+        tPB.f[lane * TSTRIDE + k] = P.out.f;
+        tPB.x[lane * TSTRIDE + k] = P.out.E;
+        if (TRANS) { tPA.f[lane * TSTRIDE + k] = P.aout.f; tPA.x[lane * TSTRIDE + k] = P.aout.e; }
+        slot_step<MEL, MODE, REV>(Q2, v, R, exp_tab, C0, t + k, in0, tag0, in1, tag1, true, ones_s, ones_e);
+        tSB.f[lane * TSTRIDE + k] = Q2.out.f;
+        tSB.x[lane * TSTRIDE + k] = Q2.out.E;
+        if (TRANS) { tSA.f[lane * TSTRIDE + k] = Q2.aout.f; tSA.x[lane * TSTRIDE + k] = Q2.aout.e; }
+        if (((t + k) & NVB_RENORM_MASK) == NVB_RENORM_MASK && TS > NVB_RENORM_MASK + 1) {
+          lane_renorm(P.S);
+          lane_renorm(Q2.S);
+        }
+      }
     }
-    if ((t & NVB_RENORM_MASK) == NVB_RENORM_MASK) {
+#ifndef NVB_EXPERIMENT_NO_STORE  // (timing experiment only, no results: what a step costs without the tile flush)
+    __syncwarp();
+    flush_tile<REV, TS>(tPB, F, X, C0, t, lane);
+    if (TRANS) flush_tile<REV, TS>(tPA, F, X, C0, t, lane);
+    if (any2_tile) {
+      flush_tile<REV, TS>(tSB, F, X, C0, t, lane);
+      if (TRANS) flush_tile<REV, TS>(tSA, F, X, C0, t, lane);
+    }
+    __syncwarp();
+#endif
+    // renormalisation every NVB_RENORM_MASK + 1 steps: at the end of the tile that completes a period (tiles longer than
+    // a period renormalise inside their step loop above)
+    if (TS <= NVB_RENORM_MASK + 1 && ((t + TS - 1) & NVB_RENORM_MASK) == NVB_RENORM_MASK) {
       lane_renorm(P.S);
       if (any2_tile) lane_renorm(Q2.S);
     }
