@@ -184,6 +184,7 @@ struct nvb_batch {
   DevBuf<int32_t> d_ref, d_ctxb, d_ctxa, d_anchors;
   // band geometry
   DevBuf<int32_t> d_bs, d_be, d_flags, d_maxw;
+  DevBuf<double> d_row_emis;   // BatchDev::row_emis
   DevBuf<int64_t> d_cell_off, d_summary;
   std::vector<int64_t> cells, w0, wn;  // per read: sum of widths over n+1 band rows, first / last width
   std::vector<int32_t> maxw, flags, no_rotation;  // no_rotation: the read needs the striped sweep (rows4.cu)
@@ -397,8 +398,11 @@ int batch_init(nvb_batch *b, const nvb_reads *r) {
   d.bandwidth = r->bandwidth; d.mel = r->min_event_length;
   d.bs = b->d_bs.p; d.be = b->d_be.p; d.cell_off = b->d_cell_off.p;
   d.flags = b->d_flags.p; d.max_width = b->d_maxw.p;
+  CU(b->d_row_emis.alloc((size_t)4 * std::max<int64_t>(b->total_ref, 1)));
+  d.row_emis = b->d_row_emis.p;
   nvbk_band(d, b->d_summary.p, st);
-  b->launches++;
+  nvbk_row_emission(b->model->dev, d, b->total_ref, nvbk_emission_scale(), b->d_row_emis.p, st);
+  b->launches += 2;
   CU(cudaGetLastError());
   std::vector<int64_t> summary((size_t)4 * n);
   CU(cudaMemcpyAsync(summary.data(), b->d_summary.p, summary.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, st));

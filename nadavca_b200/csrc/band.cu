@@ -125,7 +125,30 @@ __global__ void expected_signal_kernel(ModelDev M, BatchDev B, int64_t total, do
   out[g] = M.mean[kmer_id(M, v, i, INT32_MIN, 0)];
 }
 
+// Emission parameters of every reference position of the batch (its unmodified k-mer), one thread per position:
+// [mean, ac * S, mc * S, 0] with S = NVB_EXP_SCALE (dp3.cuh).  The sweeps read one 32-byte row when a lane takes a new
+// row pair instead of walking reference bases -> k-mer id -> three model tables (three dependent global loads in
+// front of a stalled warp).
+__global__ void row_emission_kernel(ModelDev M, BatchDev B, int64_t total, double scale, double *out) {
+  int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  int lo = 0, hi = B.n_reads;  // last read with ref_off <= g
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (B.ref_off[mid] <= g) lo = mid; else hi = mid;
+  }
+  ReadView v = read_view(B, lo);
+  const int id = kmer_id(M, v, (int)(g - B.ref_off[lo]), INT32_MIN, 0);
+  double4 row;
+  row.x = M.mean[id]; row.y = M.ac[id] * scale; row.z = M.mc[id] * scale; row.w = 0.0;
+  reinterpret_cast<double4 *>(out)[g] = row;
+}
+
 }  // namespace
+
+void nvbk_row_emission(const ModelDev &M, const BatchDev &B, int64_t total, double scale, double *d_out, cudaStream_t st) {
+  if (total > 0) row_emission_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(M, B, total, scale, d_out);
+}
 
 void nvbk_band(const BatchDev &B, int64_t *d_summary, cudaStream_t st) {
   if (B.n_reads > 0) band_kernel<<<B.n_reads, kThreads, 0, st>>>(B, d_summary);

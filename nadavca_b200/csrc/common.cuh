@@ -41,6 +41,8 @@ struct BatchDev {
   int64_t *cell_off;
   int32_t *flags;      // per read NVB_READ_* (bad band)
   int32_t *max_width;  // per read
+  const double *row_emis;  // per reference position [mu, ac * S, mc * S, 0]: Gaussian emission of the unmodified k-mer
+                           // there, ac and mc scaled for exp_ext_scaled (dp3.cuh); filled once per batch (band.cu)
 };
 
 // Inputs of the batched anchor construction (anchors.cu), CSR over reads.
@@ -66,6 +68,7 @@ struct ReadView {
   const int32_t *ref, *cb, *ca;
   const int32_t *bs, *be;
   const int64_t *coff;
+  const double *emis;  // BatchDev::row_emis of this read
 };
 
 __device__ __forceinline__ double nvb_neg_inf() { return __longlong_as_double(0xfff0000000000000LL); }
@@ -84,6 +87,7 @@ __device__ __forceinline__ ReadView read_view(const BatchDev &B, int b) {
   v.bs = B.bs + r0 + b;
   v.be = B.be + r0 + b;
   v.coff = B.cell_off + r0 + 2 * (int64_t)b;
+  v.emis = B.row_emis + 4 * r0;
   return v;
 }
 

@@ -409,6 +409,12 @@ __device__ __forceinline__ void lane_set_emission(LaneCfg &L, double mu, double 
   L.mu = mu; L.ac = ac * NVB_EXP_SCALE; L.mc = mc * NVB_EXP_SCALE;
 }
 
+// ... the same from a row of BatchDev::row_emis (already scaled)
+__device__ __forceinline__ void lane_set_emission_row(LaneCfg &L, const double *row) {
+  const double4 e = *reinterpret_cast<const double4 *>(row);
+  L.mu = e.x; L.ac = e.y; L.mc = e.z;
+}
+
 template <int MEL>
 struct LaneState {
   XD mod, w;                    // running B-row / A-row cells

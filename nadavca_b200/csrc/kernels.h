@@ -4,6 +4,9 @@
 
 // band.cu
 void nvbk_band(const BatchDev &B, int64_t *d_summary, cudaStream_t st);
+// d_out[total][4] = {mean, ac * scale, mc * scale, 0} of the k-mer at every reference position (BatchDev::row_emis)
+void nvbk_row_emission(const ModelDev &M, const BatchDev &B, int64_t total, double scale, double *d_out, cudaStream_t st);
+double nvbk_emission_scale();  // NVB_EXP_SCALE of dp3.cuh
 void nvbk_expected_signal(const ModelDev &M, const BatchDev &B, int64_t total, double *d_out, cudaStream_t st);
 
 // rows4.cu: forward + backward banded rows for reads [b0,b1): one CTA per (read, direction), stripes pipelined over

@@ -145,20 +145,18 @@ __device__ __forceinline__ void sweep_stripes(const ModelDev &M, const ReadView 
       L.ms = ls; L.me = le;
       const PairGeom pg = pair_geom<REV>(v, mode, g0);
       const int nb = (g0 > 0) ? pg.nb : pg.base;  // emission of the model row before the stripe
-      const int id = kmer_id(M, v, nb, INT32_MIN, 0);
-      lane_set_emission(L, M.mean[id], M.ac[id], M.mc[id]);
+      lane_set_emission_row(L, v.emis + 4 * (size_t)nb);
     } else if (lane <= npairs) {
       const PairGeom pg = pair_geom<REV>(v, mode, g0 + lane - 1);
-      const int id = kmer_id(M, v, pg.base, INT32_MIN, 0);
       L.role = NVB_ROLE_PAIR;
-      lane_set_emission(L, M.mean[id], M.ac[id], M.mc[id]);
+      lane_set_emission_row(L, v.emis + 4 * (size_t)pg.base);
       ws = v.bs[pg.aband]; awe = v.be[pg.aband];
       L.ms = v.bs[pg.bband]; L.me = v.be[pg.bband];
       aoff = pg.aoff; boff = pg.boff; storeA = pg.storeA && pg.hasA; storeB = 1;
       if (pg.hasA) {
         L.ws = ws; L.we = awe;
         if (mode == NVB_MODE_TRANS) {  // GetTransitionDistribution (kmer_model.cpp:64-94): constant 0.01, or 0
-          const double mo = M.mean[kmer_id(M, v, pg.nb, INT32_MIN, 0)];
+          const double mo = v.emis[4 * (size_t)pg.nb];
           const bool dead = (mo == L.mu);
           L.pc = dead ? 0.0 : 0.01 * 64.0;  // 0.01 as mantissa 0.64 and exponent -6 (an exact rescaling)
           L.kc = dead ? NVB_EZERO : -6;
@@ -405,6 +403,8 @@ SweepPlan plan_sweep(int mode, int wave_maxw, int force_warps) {
 }
 
 }  // namespace
+
+double nvbk_emission_scale() { return NVB_EXP_SCALE; }
 
 // Doubles of global scratch the striped sweep needs for its hand-off rows (0 when they fit shared memory).
 int64_t nvbk_sweep2_global_handoff_doubles(int mode, int n_reads, int wave_maxw, int force_warps) {

@@ -133,9 +133,8 @@ __device__ __forceinline__ void slot_start(Slot<MEL> &Q, const ModelDev &M, cons
   Q.t_end = pair_t_end<REV>(v, C0, g);
   const bool hasA = (MODE != NVB_MODE_PLAIN) && (REV ? (i <= n - 2) : (i >= 1));
   const int aband = REV ? i + 1 : i, bband = REV ? i : i + 1, nb = REV ? i + 1 : i - 1;
-  const int id = kmer_id(M, v, i, INT32_MIN, 0);
   Q.L.role = NVB_ROLE_PAIR;
-  lane_set_emission(Q.L, M.mean[id], M.ac[id], M.mc[id]);
+  lane_set_emission_row(Q.L, v.emis + 4 * (size_t)i);
   Q.L.ms = v.bs[bband]; Q.L.me = v.be[bband];
   if (MODE == NVB_MODE_TRANS) {
     Q.aoff = trans_row_off(v, REV ? 2 * i + 1 : 2 * i);
@@ -147,7 +146,7 @@ __device__ __forceinline__ void slot_start(Slot<MEL> &Q, const ModelDev &M, cons
     Q.L.ws = v.bs[aband]; Q.L.we = v.be[aband];
     if (MODE == NVB_MODE_TRANS) {  // GetTransitionDistribution (kmer_model.cpp:64-94): constant 0.01, or 0
       Q.ws = Q.L.ws; Q.awe = Q.L.we;
-      const double mo = M.mean[kmer_id(M, v, nb, INT32_MIN, 0)];
+      const double mo = v.emis[4 * (size_t)nb];
       const bool dead = (mo == Q.L.mu);
       Q.L.pc = dead ? 0.0 : 0.01 * 64.0;  // 0.01 as mantissa 0.64 and exponent -6 (an exact rescaling)
       Q.L.kc = dead ? NVB_EZERO : -6;
