@@ -427,17 +427,12 @@ int batch_init(nvb_batch *b, const nvb_reads *r) {
 // the pipelined stripes (rows4.cu).
 int run_sweep(nvb_batch *b, Workspace &ws, int mode, const Wave &w, cudaStream_t st) {
   const ModelDev &M = b->model->dev;
-  // Measured on B200 (profiles/r02r_sweep_schedules.txt): the rotating wavefront needs half the warp-steps but ~1.4x the
-  // instructions per step and one warp per direction instead of two.  It wins once its warps (2 per read) fill a good
-  // part of one resident wave of the GPU (16 warps per SM at its 128 registers) -- 40 % for the plain sweep (500 reads:
-  // 13.8 against 14.1 ms), 60 % for the wobble sweep (500 reads: 21.1 against 16.5 ms, 1000 reads: 25.6 against 29.2) --
-  // and keeps winning with several waves (2000 reads: 30.2 / 45.9 ms against 39.7 / 47.3); with fewer reads the
-  // striped sweep hides latency better.
-  // (the transition sweep stores twice the rows and loses by rotating: 46 against 32 ms at 1000 reads)
-  const int items = 2 * (w.b1 - w.b0);
-  const int resident = b->model->sm_count * 16;
-  const int need_pct = mode == NVB_MODE_PLAIN ? 40 : 60;
-  bool rotate = mode != NVB_MODE_TRANS && w.maxw <= 640 && 100 * (int64_t)items >= (int64_t)need_pct * resident;
+  // Measured on B200 (profiles/r02y_sweep_schedules.txt, 32 .. 2000 reads): since the round-2 work on its step loop the
+  // rotating wavefront wins at every batch size and in every mode (one read: 7.3 against 10.8 ms for the plain sweep;
+  // 1000 reads: 13.2 / 29.2 / 16.4 ms against 23.7 / 30.7 / 27.3 ms plain / transitions / wobble), so it runs whenever
+  // the band rows fit its signal window (640 columns) and the band kernel found no read that needs a third slot; the
+  // striped sweep keeps the wide and the irregular bands.
+  bool rotate = w.maxw <= 640;
   if (g_opt.sweep != NVB_SWEEP_AUTO) rotate = w.maxw <= 640 && g_opt.sweep == NVB_SWEEP_ROTATE;
   for (int i = w.b0; i < w.b1 && rotate; i++) rotate = !b->no_rotation[i];
   if (rotate)
