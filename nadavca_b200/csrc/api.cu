@@ -431,8 +431,13 @@ int run_sweep(nvb_batch *b, Workspace &ws, int mode, const Wave &w, cudaStream_t
   // rotating wavefront wins at every batch size and in every mode (one read: 7.3 against 10.8 ms for the plain sweep;
   // 1000 reads: 13.2 / 29.2 / 16.4 ms against 23.7 / 30.7 / 27.3 ms plain / transitions / wobble), so it runs whenever
   // the band rows fit its signal window (640 columns) and the band kernel found no read that needs a third slot; the
-  // striped sweep keeps the wide and the irregular bands.
-  bool rotate = w.maxw <= 640;
+  // striped sweep keeps the wide and the irregular bands.  One exception: band rows wider than the 352 steps a lane has
+  // per row pair keep the second slot of every lane busy (two step bodies per step); then the stripes are faster for
+  // the transition and wobble sweeps of SMALL batches (64 reads, band 200: 13.6 / 12.3 ms against 17.6 / 13.2 ms), the
+  // rotation still for large ones (512 reads: 22.2 / 17.4 ms against 27.2 / 24.5 ms).
+  const int items = 2 * (w.b1 - w.b0);
+  const int resident = b->model->sm_count * 16;  // sweep warps of one resident wave
+  bool rotate = w.maxw <= 640 && (w.maxw <= 352 || mode == NVB_MODE_PLAIN || 4 * items >= resident);
   if (g_opt.sweep != NVB_SWEEP_AUTO) rotate = w.maxw <= 640 && g_opt.sweep == NVB_SWEEP_ROTATE;
   for (int i = w.b0; i < w.b1 && rotate; i++) rotate = !b->no_rotation[i];
   if (rotate)
