@@ -91,6 +91,12 @@ __device__ __forceinline__ void cp_async8(void *dst_smem, const void *src) {
                : "memory");
 }
 
+// 16 bytes global -> shared past L1 (the record words were written by this CTA a moment ago)
+__device__ __forceinline__ void cp_async16_cg(void *dst_smem, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
+}
+
 template <int PK, int D>
 __global__ void __launch_bounds__(256) path2_kernel(BatchDev B, int mode, int b0, int n_items, const int64_t *mat_base,
                                                     const double *score, uint32_t *records, const int64_t *rec_base,
@@ -252,7 +258,13 @@ __global__ void __launch_bounds__(256) path2_kernel(BatchDev B, int mode, int b0
     fill_geo(lo, hi - lo + 2);  // geo[i] = row lo + i, up to row hi + 1 (empty when hi + 1 == R)
     if (staged) {
       const uint32_t *src = FL + (int64_t)lo * words_per_row;
-      for (int i = threadIdx.x; i < (hi - lo + 1) * words_per_row; i += blockDim.x) stage[i] = __ldcg(src + i);
+      // asynchronous 16-byte copies, all in flight at once: a load -> store loop left the CTA waiting on one L2
+      // round trip per word and thread (24 % of the kernel's stall samples, ncu r02x).  Rows are whole chunks of 32
+      // words and the record planes start on 128-byte boundaries, so every piece is aligned.
+      const int words = (hi - lo + 1) * words_per_row;
+      for (int i = 4 * threadIdx.x; i < words; i += 4 * blockDim.x) cp_async16_cg(stage + i, src + i);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     if (warp != 0 || no_path) continue;
