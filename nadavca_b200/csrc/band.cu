@@ -126,7 +126,7 @@ __global__ void expected_signal_kernel(ModelDev M, BatchDev B, int64_t total, do
 }
 
 // Emission parameters of every reference position of the batch (its unmodified k-mer), one thread per position:
-// [mean, ac * S, mc * S, 0] with S = NVB_EXP_SCALE (dp3.cuh).  The sweeps read one 32-byte row when a lane takes a new
+// [mean, ac * S, mc * S, same-mean flags] with S = NVB_EXP_SCALE (dp3.cuh).  The sweeps read one 32-byte row when a lane takes a new
 // row pair instead of walking reference bases -> k-mer id -> three model tables (three dependent global loads in
 // front of a stalled warp).
 __global__ void row_emission_kernel(ModelDev M, BatchDev B, int64_t total, double scale, double *out) {
@@ -138,9 +138,16 @@ __global__ void row_emission_kernel(ModelDev M, BatchDev B, int64_t total, doubl
     if (B.ref_off[mid] <= g) lo = mid; else hi = mid;
   }
   ReadView v = read_view(B, lo);
-  const int id = kmer_id(M, v, (int)(g - B.ref_off[lo]), INT32_MIN, 0);
+  const int i = (int)(g - B.ref_off[lo]);
+  const int id = kmer_id(M, v, i, INT32_MIN, 0);
+  const double mean = M.mean[id];
+  // bit 0 / 1: the position before / after has the same mean (GetTransitionDistribution, kmer_model.cpp:64-94: the
+  // transition between two such rows has probability 0)
+  int same = 0;
+  if (i >= 1 && M.mean[kmer_id(M, v, i - 1, INT32_MIN, 0)] == mean) same |= 1;
+  if (i + 1 < v.n && M.mean[kmer_id(M, v, i + 1, INT32_MIN, 0)] == mean) same |= 2;
   double4 row;
-  row.x = M.mean[id]; row.y = M.ac[id] * scale; row.z = M.mc[id] * scale; row.w = 0.0;
+  row.x = mean; row.y = M.ac[id] * scale; row.z = M.mc[id] * scale; row.w = (double)same;
   reinterpret_cast<double4 *>(out)[g] = row;
 }
 

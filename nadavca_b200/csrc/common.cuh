@@ -41,7 +41,7 @@ struct BatchDev {
   int64_t *cell_off;
   int32_t *flags;      // per read NVB_READ_* (bad band)
   int32_t *max_width;  // per read
-  const double *row_emis;  // per reference position [mu, ac * S, mc * S, 0]: Gaussian emission of the unmodified k-mer
+  const double *row_emis;  // per reference position [mu, ac * S, mc * S, same-mean flags]: Gaussian emission of the unmodified k-mer
                            // there, ac and mc scaled for exp_ext_scaled (dp3.cuh); filled once per batch (band.cu)
 };
 

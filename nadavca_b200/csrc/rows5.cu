@@ -54,8 +54,40 @@ __host__ __device__ constexpr size_t tile_bytes(int ts) {
 }
 // tiles per warp: the B rows of the two slots, plus their A rows in the transition sweep (the only one that stores them)
 __host__ __device__ constexpr int tiles_per_warp(int mode) { return mode == NVB_MODE_TRANS ? 4 : 2; }
+// Parameters of the NEXT row pair of a lane, staged in shared memory by cp.async while the lane's current pair is
+// still running (~350 steps ahead): band rows i and i+1, their cell offsets and the emission row of position i.  A lane
+// that takes a new pair reads them back with shared-memory latency; fetched at that moment from global memory they
+// left the whole warp waiting (long-scoreboard stalls were 29 % of the stall cycles of the sweep, ncu r02z).
+struct PairRec {
+  int bs0, bs1, be0, be1;
+  long long coff0, coff1;
+  double mu, ac, mc, flags;  // BatchDev::row_emis[i]
+};
+static_assert(sizeof(PairRec) == 64, "PairRec layout");
+// per warp: store tiles | signal ring | 32 PairRec
+__host__ __device__ constexpr size_t rec_offset(int mode) {
+  return ((tiles_per_warp(mode) * tile_bytes(tile_steps(mode)) + ring_bytes(8) + 15) / 16) * 16;
+}
 __host__ __device__ constexpr size_t warp_bytes(int mode) {  // keeps every ring 256-byte aligned
-  return ((tiles_per_warp(mode) * tile_bytes(tile_steps(mode)) + ring_bytes(8) + 255) / 256) * 256;
+  return ((rec_offset(mode) + NVB_WARP * sizeof(PairRec) + 255) / 256) * 256;
+}
+
+__device__ __forceinline__ void rec_prefetch(PairRec *rec, const ReadView &v, int i) {
+  const unsigned a = smem_u32(rec);
+  const int32_t *bs = v.bs + i, *be = v.be + i;
+  const int64_t *co = v.coff + i;
+  const double *em = v.emis + 4 * (size_t)i;
+  asm volatile(
+      "cp.async.ca.shared.global [%0], [%1], 4;\n"
+      "cp.async.ca.shared.global [%0 + 4], [%1 + 4], 4;\n"
+      "cp.async.ca.shared.global [%0 + 8], [%2], 4;\n"
+      "cp.async.ca.shared.global [%0 + 12], [%2 + 4], 4;\n"
+      "cp.async.ca.shared.global [%0 + 16], [%3], 8;\n"
+      "cp.async.ca.shared.global [%0 + 24], [%3 + 8], 8;\n"
+      "cp.async.ca.shared.global [%0 + 32], [%4], 16;\n"
+      "cp.async.ca.shared.global [%0 + 48], [%4 + 16], 16;\n"
+      "cp.async.commit_group;\n" ::"r"(a), "l"(bs), "l"(be), "l"(co), "l"(em)
+      : "memory");
 }
 
 template <bool REV, int TS>
@@ -123,31 +155,33 @@ __device__ __forceinline__ int sample_index(const ReadView &v, int C0, int g, in
 }
 
 template <int MEL, int MODE, bool REV>
-__device__ __forceinline__ void slot_start(Slot<MEL> &Q, const ModelDev &M, const ReadView &v, const SignalRing<8> &R,
-                                           unsigned exp_tab, int C0, int g, int t) {
+__device__ __forceinline__ void slot_start(Slot<MEL> &Q, const ReadView &v, const SignalRing<8> &R, unsigned exp_tab,
+                                           const PairRec *rec, long long coff1, int C0, int g, int t) {
   const int n = v.n;
   const int i = pair_base<REV>(n, g);
   const double C_E2 = 0.1353352832366127;  // exp(-2): the "/ 2" of kmer_model.cpp:60 is "- 2.0" in log space
+  asm volatile("cp.async.wait_group 0;" ::: "memory");  // this lane's record of pair g (rec_prefetch) has landed
+  const PairRec r = *rec;
   slot_clear(Q);
   Q.pair = g;
-  Q.t_end = pair_t_end<REV>(v, C0, g);
+  Q.t_end = REV ? (C0 - r.bs0) + g : (r.be1 - C0) + g;  // pair_t_end
   const bool hasA = (MODE != NVB_MODE_PLAIN) && (REV ? (i <= n - 2) : (i >= 1));
-  const int aband = REV ? i + 1 : i, bband = REV ? i : i + 1, nb = REV ? i + 1 : i - 1;
+  // A-row on band row (REV ? i + 1 : i), B-row on band row (REV ? i : i + 1)
   Q.L.role = NVB_ROLE_PAIR;
-  lane_set_emission_row(Q.L, v.emis + 4 * (size_t)i);
-  Q.L.ms = v.bs[bband]; Q.L.me = v.be[bband];
-  if (MODE == NVB_MODE_TRANS) {
-    Q.aoff = trans_row_off(v, REV ? 2 * i + 1 : 2 * i);
-    Q.boff = trans_row_off(v, REV ? 2 * i : 2 * i + 1);
+  Q.L.mu = r.mu; Q.L.ac = r.ac; Q.L.mc = r.mc;
+  Q.L.ms = REV ? r.bs0 : r.bs1; Q.L.me = REV ? r.be0 : r.be1;
+  if (MODE == NVB_MODE_TRANS) {  // trans_row_off(): rows 2i / 2i+1 live on band rows i / i+1
+    const long long even = r.coff0 + r.coff1 - coff1, odd = 2 * r.coff1 - coff1;
+    Q.aoff = REV ? odd : even;
+    Q.boff = REV ? even : odd;
   } else {
-    Q.boff = v.coff[bband];
+    Q.boff = REV ? r.coff0 : r.coff1;
   }
   if (hasA) {
-    Q.L.ws = v.bs[aband]; Q.L.we = v.be[aband];
+    Q.L.ws = REV ? r.bs1 : r.bs0; Q.L.we = REV ? r.be1 : r.be0;
     if (MODE == NVB_MODE_TRANS) {  // GetTransitionDistribution (kmer_model.cpp:64-94): constant 0.01, or 0
       Q.ws = Q.L.ws; Q.awe = Q.L.we;
-      const double mo = v.emis[4 * (size_t)nb];
-      const bool dead = (mo == Q.L.mu);
+      const bool dead = ((int)r.flags >> (REV ? 1 : 0)) & 1;  // same mean as the row on the other side of the transition
       Q.L.pc = dead ? 0.0 : 0.01 * 64.0;  // 0.01 as mantissa 0.64 and exponent -6 (an exact rescaling)
       Q.L.kc = dead ? NVB_EZERO : -6;
     } else {
@@ -219,7 +253,7 @@ __device__ __forceinline__ void write_meta(const StoreTile &tb, const StoreTile 
 
 template <int MEL, int MODE, bool REV>
 __device__ void sweep_rotate(const ModelDev &M, const ReadView &v, double *F, int32_t *X, int lane,
-                             const StoreTile (&tiles)[4], const SignalRing<8> &R, unsigned exp_tab) {
+                             const StoreTile (&tiles)[4], const SignalRing<8> &R, unsigned exp_tab, PairRec *recs) {
   const int n = v.n;
   constexpr bool TRANS = (MODE == NVB_MODE_TRANS);
   constexpr int TS = tile_steps(MODE), TSTRIDE = TS + 1;
@@ -241,6 +275,9 @@ __device__ void sweep_rotate(const ModelDev &M, const ReadView &v, double *F, in
   slot_clear(Q2);
   int next_g = lane;                                   // next pair this lane will take
   int next_start = (next_g < n) ? pair_t_start<REV>(v, C0, next_g) : 0x7fffffff;
+  PairRec *rec = recs + lane;                          // parameters of pair next_g, in flight or landed
+  if (next_g < n) rec_prefetch(rec, v, pair_base<REV>(n, next_g));
+  const long long coff1 = TRANS ? v.coff[1] : 0;
   bool any2_tile = false;                              // some lane had a live second slot during this tile
 
   // One iteration per store tile: slot management, then TS steps (two copies of the step loop, with and without the
@@ -275,10 +312,11 @@ __device__ void sweep_rotate(const ModelDev &M, const ReadView &v, double *F, in
         }
       }
       if (starting) {
-        if (P.pair < 0) slot_start<MEL, MODE, REV>(P, M, v, R, exp_tab, C0, next_g, t);
-        else slot_start<MEL, MODE, REV>(Q2, M, v, R, exp_tab, C0, next_g, t);  // the band kernel guarantees Q2 is free
+        if (P.pair < 0) slot_start<MEL, MODE, REV>(P, v, R, exp_tab, rec, coff1, C0, next_g, t);
+        else slot_start<MEL, MODE, REV>(Q2, v, R, exp_tab, rec, coff1, C0, next_g, t);  // the band kernel guarantees Q2 is free
         next_g += NVB_WARP;
         next_start = (next_g < n) ? pair_t_start<REV>(v, C0, next_g) : 0x7fffffff;
+        if (next_g < n) rec_prefetch(rec, v, pair_base<REV>(n, next_g));  // its record was read into the slot above
       }
       any2_tile = __any_sync(NVB_FULL, Q2.pair >= 0);
       write_meta(tPB, tPA, P, lane, TRANS);
@@ -365,14 +403,16 @@ __global__ void __launch_bounds__(64, NVB_ROT_MIN_BLOCKS) sweep5_kernel(ModelDev
   // signal ring (dp3.cuh) behind the four store tiles: 8 chunks of 32 samples + 8 mbarriers, filled by TMA bulk copies
   SignalRing<8> R;
   ring_init(R, base + tiles_per_warp(MODE) * tile_bytes(tile_steps(MODE)), B.signal, B.sig_off[b], B.sig_off[B.n_reads], lane);
-  if (item & 1) sweep_rotate<MEL, MODE, true>(M, v, sF + mb, sX + mb, lane, tiles, R, exp_tab);
-  else sweep_rotate<MEL, MODE, false>(M, v, pF + mb, pX + mb, lane, tiles, R, exp_tab);
+  PairRec *recs = reinterpret_cast<PairRec *>(base + rec_offset(MODE));
+  if (item & 1) sweep_rotate<MEL, MODE, true>(M, v, sF + mb, sX + mb, lane, tiles, R, exp_tab, recs);
+  else sweep_rotate<MEL, MODE, false>(M, v, pF + mb, pX + mb, lane, tiles, R, exp_tab, recs);
 }
 
 template <int MEL, int MODE>
 void launch_mode(const ModelDev &M, const BatchDev &B, int b0, int n_items, const int64_t *mb, double *pF, int32_t *pX,
                  double *sF, int32_t *sX, cudaStream_t st) {
-  const int warps = 2;  // 2 x (2 tiles x 4.2 KB + 2 KB ring) = 21 KB per CTA (38 KB in the transition sweep)
+  const int warps = 2;  // 2 x (2 tiles x 4.2 KB + 2 KB ring + 2 KB pair records) = 25 KB per CTA (42 KB in the transition
+                        // sweep): 8 CTAs per SM (5) beside the 2 KB exp table and the 1 KB the driver reserves per CTA
   const size_t smem = (size_t)warps * warp_bytes(MODE);
   sweep5_kernel<MEL, MODE><<<(n_items + warps - 1) / warps, warps * NVB_WARP, smem, st>>>(M, B, b0, n_items, mb, pF, pX,
                                                                                          sF, sX);
