@@ -1,5 +1,6 @@
-"""A small batch through every DP entry point, for compute-sanitizer (memcheck / racecheck / initcheck):
-  compute-sanitizer --tool memcheck python tools/sanitize_small.py [reads] [bases]"""
+"""A small batch through every DP entry point (both band widths, min_event_length 0 and 2): a quick smoke run, and
+the driver for `compute-sanitizer --tool memcheck python tools/sanitize_small.py [reads] [bases]` where a sanitizer is
+available (it is closed on the round-2 GPU pool)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
