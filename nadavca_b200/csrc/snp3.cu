@@ -11,6 +11,15 @@
 
 namespace {
 
+// Renormalisation period of the SNP kernel: 16 steps instead of the 8 of the sweeps (dp3.cuh NVB_RENORM_MASK).  A task
+// is a chain of at most 8 lanes, so stale-mantissa slack compounds over at most 8 hops: with <= 2 bits per step and hop
+// (emission mantissa < 2, one addition) 16 steps stay below 2^256, far inside the double range; the sweeps, whose chains
+// are 32 lanes long, keep 8.  Measured: 71.1 -> 69.8 ms at 1000 reads (the renormalisation was 6.5 % of the kernel's
+// instructions), parity suite and fuzz unchanged (profiles/r02ad).
+#ifndef NVB_SNP_RENORM_MASK
+#define NVB_SNP_RENORM_MASK 15
+#endif
+
 template <int MEL, int MODE>
 __global__ void __launch_bounds__(128) snp3_kernel(ModelDev M, BatchDev B, int b0, int b1, int64_t g0, int64_t n_tasks,
                                                    int LT, int TPW, const int64_t *mat_base, const double *pF,
@@ -116,7 +125,7 @@ __global__ void __launch_bounds__(128) snp3_kernel(ModelDev M, BatchDev B, int b
     } else if (!passes) {
       res.f = 0.0; res.E = NVB_EZERO;
     }
-    if ((t & NVB_RENORM_MASK) == NVB_RENORM_MASK) lane_renorm(S);
+    if ((t & NVB_SNP_RENORM_MASK) == NVB_SNP_RENORM_MASK) lane_renorm(S);
   }
   if (is_join) {
     xd_renorm(S.mod);  // canonical mantissa
