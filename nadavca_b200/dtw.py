@@ -304,9 +304,12 @@ def set_sweep_schedule(schedule):
 
 
 def trim_memory(device=None):
-    """Hand the library's cached device blocks back to the driver (nvb_trim_memory)."""
+    """Hand the library's cached device blocks back to the driver (nvb_trim_memory) and free the pinned staging
+    buffers of the device normalisation."""
+    from .read import trim_staging
     lib = _cabi.require_device()
     _cabi.check(lib.nvb_trim_memory(_current_device() if device is None else int(device)), 'nvb_trim_memory')
+    trim_staging()
 
 
 def measure_fp64_fma_rate(device=0):

@@ -316,8 +316,15 @@ class ProbabilityEstimator:
             if stage is None:
                 return [None] * len(reads) if independent else []
             groups, group_off, out, cov = stage
-            probabilities = out.cpu().numpy()
-            coverage = cov.cpu().numpy().astype(int)
+            # D2H through a cached pinned buffer; the Chunks below take their own copies of their rows
+            from .read import _staging
+            import torch
+            count = out.numel()
+            pinned = _staging('probabilities', count)
+            pinned[:count].copy_(out.reshape(-1), non_blocking=True)
+            coverage = cov.cpu().numpy().astype(int)  # (synchronises the stream: the pinned copy has landed too)
+            torch.cuda.current_stream(out.device).synchronize()
+            probabilities = pinned.numpy()[:count].reshape(tuple(out.shape))
             self.last_stats = {'launches': sum(batch.launch_count for batch, _ in subs) + 1,
                                'groups': len(groups), 'positions': int(group_off[-1]), 'sub_batches': len(subs)}
         finally:

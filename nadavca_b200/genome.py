@@ -7,8 +7,10 @@ _LUT = numpy.full(256, -1, dtype=numpy.int32)
 for _base, _index in inv_alphabet.items():
     _LUT[ord(_base)] = _index
 _COMP = numpy.arange(256, dtype=numpy.uint8)
+_HAS_COMP = numpy.zeros(256, dtype=bool)
 for _base, _other in complement.items():
     _COMP[ord(_base)] = ord(_other)
+    _HAS_COMP[ord(_base)] = True
 
 
 def _as_bytes(sequence):
@@ -51,9 +53,9 @@ class Genome:
     def reverse_complement(sequence):
         """genome.py:19-23: complement every base and reverse; returns an array of 1-char strings."""
         raw = _as_bytes(sequence)
-        for value in numpy.unique(raw):
-            if chr(int(value)) not in complement:
-                raise KeyError(chr(int(value)))
+        known = _HAS_COMP[raw]
+        if not known.all():  # the reference's dict lookup raises KeyError on the first base it does not know
+            raise KeyError(chr(int(raw[int(numpy.argmin(known))])))
         return _COMP[raw][::-1].astype(numpy.uint32).view('U1')  # UCS4 code points -> array of 1-char strings
 
     @staticmethod

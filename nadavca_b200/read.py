@@ -61,15 +61,18 @@ class Read:
         With `device` (a CUDA ordinal) the pooled samples are normalised ON THE GPU: exact radix select of the two
         medians (8 histogram passes each, the 256-bin histograms all-reduced over `process_group` when given) and the
         clip kernel; the result is bit-identical to the host path."""
-        values = numpy.concatenate([numpy.asarray(read.raw_signal, dtype=float) for read in reads]) \
-            if len(reads) else numpy.zeros(0)
         if device is not None:
-            normalized = _normalize_on_device(values, int(device), process_group)
+            # the pooled samples go through two cached pinned staging buffers (H2D and D2H at PCIe speed instead of
+            # pageable copies); every read gets its own copy of its slice
+            normalized = _normalize_on_device([numpy.asarray(read.raw_signal, dtype=float) for read in reads],
+                                              int(device), process_group)
             start = 0
             for read in reads:
-                read.normalized_signal = normalized[start:start + len(read.raw_signal)]
+                read.normalized_signal = normalized[start:start + len(read.raw_signal)].copy()
                 start += len(read.raw_signal)
             return
+        values = numpy.concatenate([numpy.asarray(read.raw_signal, dtype=float) for read in reads]) \
+            if len(reads) else numpy.zeros(0)
         if process_group is None:
             shift = float(numpy.median(values))
             scale = float(numpy.median(abs(values - shift)))
@@ -242,9 +245,28 @@ def fit_splines_async(jobs, workers=None):
     return _FIT_POOL[0].submit(jobs)
 
 
+_STAGING = {}
+
+
+def _staging(name, count):
+    """A cached pinned float64 host buffer of at least `count` elements (grow-only; `trim_staging()` frees them)."""
+    import torch
+    buf = _STAGING.get(name)
+    if buf is None or buf.numel() < count:
+        buf = torch.empty(max(int(count), 1), dtype=torch.float64).pin_memory()
+        _STAGING[name] = buf
+    return buf
+
+
+def trim_staging():
+    """Release the pinned staging buffers of the device normalisation."""
+    _STAGING.clear()
+
+
 def _normalize_on_device(values, device, process_group=None):
     """clip((values - median) / MAD, -5, 5) computed on CUDA device `device` (csrc/select.cu); `values` is this
-    rank's share of the pooled samples."""
+    rank's share of the pooled samples: one float64 array or a list of them (concatenated straight into the pinned
+    upload buffer).  The result is a view of a cached pinned buffer: copy what you keep."""
     import ctypes
     import torch
     from . import _cabi
@@ -252,15 +274,19 @@ def _normalize_on_device(values, device, process_group=None):
     dev = torch.device('cuda', device)
     stream = torch.cuda.current_stream(dev)
     sp = ctypes.c_void_p(stream.cuda_stream)
-    d_values = torch.from_numpy(numpy.ascontiguousarray(values, dtype=numpy.float64)).to(dev)
-    n_local = d_values.numel()
+    parts = values if isinstance(values, (list, tuple)) else [numpy.asarray(values, dtype=numpy.float64).reshape(-1)]
+    n_local = int(sum(len(p) for p in parts))
+    up = _staging('up', n_local)
+    if n_local:
+        numpy.concatenate(parts, out=up.numpy()[:n_local])
+    d_values = up[:n_local].to(dev, non_blocking=True)
     dist = None
     if process_group is not None:
         import torch.distributed as dist
     count = torch.tensor([n_local], dtype=torch.int64, device=dev)
     if dist is not None:
         dist.all_reduce(count, group=process_group)
-    n = int(count.item())
+    n = int(count.item())  # (synchronises: the upload buffer may be reused from here on)
     if n == 0:
         return numpy.zeros(0)
 
@@ -291,7 +317,10 @@ def _normalize_on_device(values, device, process_group=None):
     d_out = torch.empty_like(d_values)
     _cabi.check(lib.nvb_normalize_clip_d(device, ctypes.c_void_p(d_values.data_ptr()), n_local, shift, scale, -5.0, 5.0,
                                          ctypes.c_void_p(d_out.data_ptr()), sp), 'nvb_normalize_clip_d')
-    return d_out.cpu().numpy()
+    down = _staging('down', n_local)
+    down[:n_local].copy_(d_out, non_blocking=True)
+    stream.synchronize()
+    return down.numpy()[:n_local]
 
 
 def _ordered_keys(values):
