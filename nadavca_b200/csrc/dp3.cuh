@@ -510,24 +510,22 @@ __device__ __forceinline__ void lane_update(const LaneCfg &L, LaneState<MEL> &S,
     kb = join ? 0 : kk;
     push = xd_make(wout.f * sF, wout.e + sX);
   }
-  // B[c] = e(c-1) * B[c-1] + (product of the last m emissions) * A[c-m]
-  XD popped;
+  // B[c] = e(c-1) * B[c-1] + (product of the last m emissions) * A[c-m], factored as
+  //   B[c] = e(c-1) * (B[c-1] + Q_{m-1}[c-1]),  Q_i[c] = e(c-1) * Q_{i-1}[c-1],  Q_0[c] = A[c]:
+  // the oldest value in flight joins the cell BEFORE the emission is applied, so a step costs m multiplications
+  // instead of m + 1, and every in-flight value is computed straight into its next slot (no shifting moves: the
+  // delay line of the unfactored form cost 6 register moves per step at m = 2).  S.q[0] = A of the previous step,
+  // S.q[i] = Q_i.
+  static_assert(PH < 0, "the delay line needs no phase any more");
   if (MEL == 0) {
-    popped = push;
+    S.mod = xd_add(xd_make(pb * S.mod.f, S.mod.e + kb), push);
   } else {
+    const XD joined = xd_add(S.mod, S.q[MEL - 1]);
+    S.mod = xd_make(pb * joined.f, joined.e + kb);
 #pragma unroll
-    for (int i = 0; i < MEL; i++) { S.q[i].f *= pb; S.q[i].e += kb; }
-    if (PH >= 0) {  // ring: slot PH was pushed MEL steps ago
-      popped = S.q[PH >= 0 ? PH : 0];
-      S.q[PH >= 0 ? PH : 0] = push;
-    } else {        // PH < 0: plain delay line (callers that do not unroll their step loop)
-      popped = S.q[MEL - 1];
-#pragma unroll
-      for (int i = MEL - 1; i > 0; i--) S.q[i] = S.q[i - 1];
-      S.q[0] = push;
-    }
+    for (int i = MEL - 1; i > 0; i--) S.q[i] = xd_make(pb * S.q[i - 1].f, S.q[i - 1].e + kb);
+    S.q[0] = push;
   }
-  S.mod = xd_add(xd_make(pb * S.mod.f, S.mod.e + kb), popped);
   const bool inb = (FWD_ONLY && MODE == NVB_MODE_WOBBLE) ? (c >= L.ms) : ((c >= L.ms) && (c <= L.me));
   out.f = inb ? S.mod.f : 0.0;
   out.E = inb ? S.mod.e : NVB_EZERO;

@@ -107,25 +107,31 @@ __global__ void __launch_bounds__(128) snp3_kernel(ModelDev M, BatchDev B, int b
   const bool is_loader = L.role == NVB_ROLE_LOADER, is_join = L.role == NVB_ROLE_JOIN;
   const bool reads_row = is_loader || is_join;
   const bool passes = L.role == NVB_ROLE_PAIR;  // lanes whose B-row cell feeds the next lane
-  for (int t = 0; t < T; t++) {
-    const int c = C0 + (t - ri);
-    const double x = __ldg(sig + min(max(c - 1, 0), N - 1));
-    LaneOut in = shfl_up_out<MODE>(res);
-    double rF = 0.0;
-    int rX = NVB_EZERO;
-    if (reads_row && c >= L.ms && c <= L.me) {
-      rF = __ldg(rowF + (c - L.ms));
-      rX = __ldg(rowX + (c - L.ms));
+  // Blocks of NVB_SNP_RENORM_MASK + 1 steps with the renormalisation between them: a test inside the step loop made
+  // every loop-carried value take a register move per step (the two paths had to meet in the same registers).
+  for (int t0 = 0; t0 < T; t0 += NVB_SNP_RENORM_MASK + 1) {
+    const int t1 = min(t0 + NVB_SNP_RENORM_MASK + 1, T);
+#pragma unroll 1
+    for (int t = t0; t < t1; t++) {
+      const int c = C0 + (t - ri);
+      const double x = __ldg(sig + min(max(c - 1, 0), N - 1));
+      LaneOut in = shfl_up_out<MODE>(res);
+      double rF = 0.0;
+      int rX = NVB_EZERO;
+      if (reads_row && c >= L.ms && c <= L.me) {
+        rF = __ldg(rowF + (c - L.ms));
+        rX = __ldg(rowX + (c - L.ms));
+      }
+      XD aout;
+      // JOIN lanes multiply their A-row cell by the closing suffix cell, every other lane by (1.0, 0)
+      lane_step<MEL, MODE, true, -1, false>(L, S, exp_tab, c, x, in, is_join ? rF : 1.0, is_join ? rX : 0, res, aout);
+      if (is_loader) {  // the loader's output is the stored prefix row (zero outside its band)
+        res.f = rF; res.E = rX;
+      } else if (!passes) {
+        res.f = 0.0; res.E = NVB_EZERO;
+      }
     }
-    XD aout;
-    // JOIN lanes multiply their A-row cell by the closing suffix cell, every other lane by (1.0, 0)
-    lane_step<MEL, MODE, true, -1, false>(L, S, exp_tab, c, x, in, is_join ? rF : 1.0, is_join ? rX : 0, res, aout);
-    if (is_loader) {  // the loader's output is the stored prefix row (zero outside its band)
-      res.f = rF; res.E = rX;
-    } else if (!passes) {
-      res.f = 0.0; res.E = NVB_EZERO;
-    }
-    if ((t & NVB_SNP_RENORM_MASK) == NVB_SNP_RENORM_MASK) lane_renorm(S);
+    lane_renorm(S);
   }
   if (is_join) {
     xd_renorm(S.mod);  // canonical mantissa
