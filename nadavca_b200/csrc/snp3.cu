@@ -97,8 +97,7 @@ __global__ void __launch_bounds__(128) snp3_kernel(ModelDev M, BatchDev B, int b
       }
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) T = max(T, __shfl_xor_sync(NVB_FULL, T, o));
+  T = __reduce_max_sync(NVB_FULL, T);  // (a REDUX result is warp-uniform for the compiler as well: uniform loop bounds)
 
   LaneState<MEL> S;
   lane_reset(S);
