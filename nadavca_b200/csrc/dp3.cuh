@@ -26,7 +26,10 @@
 // wavefront step): polynomial coefficients come from the constant bank as DFMA operands instead of 2 UMOV each,
 // the JOIN role shares the B-row code (emission 1, inflow multiplied by the suffix cell), rows without an A-row are
 // handled by data (zero mixture weight, open band) instead of a divergent branch, and the kernel is specialised on the
-// row mode so the plain sweep carries no A-row code and the transition sweep no mixture.
+// row mode so the plain sweep carries no A-row code and the transition sweep no mixture.  Round 2 (ncu source page,
+// DESIGN.md section 6): the emission exp takes a scaled argument (no hi/lo reduction, no re-materialised constants),
+// the B-row recurrence is factored so that a step costs m multiplications and no delay-line moves, and the step loops
+// carry no renormalisation / tile tests.
 #pragma once
 #include "common.cuh"
 
@@ -442,10 +445,6 @@ struct LaneOut {
 // cell the running sum of Node::TotalLikelihood (node.cpp:31-37), delayed by MEL steps; other lanes pass (1.0, 0).
 // `aout` receives the A-row cell (for callers that store it).
 //
-// PH >= 0 = step index mod MEL: the A-row cells in flight to the B-row live in a ring (slot PH is the one pushed MEL
-// steps ago) for callers that unroll their step loop MEL times.  PH < 0: a plain shifting delay line for rolled loops.
-// Both kernels use PH < 0: unrolling saved ~6 register moves per step but cost registers -- the SNP kernel dropped
-// from 7 to 6 resident CTAs per SM and got 12 % slower (measured), the sweeps would lose their 14 CTAs per SM.
 // FWD_ONLY (forward-only callers with wobble rows): the A-row needs only its upper band limit (below the band its
 // inflow is already zero) and the B-row output only its lower one (above the band the consumer's own A-row limit cuts
 // it off); lanes without an output use ms = INT_MAX.  Measured neutral on the SNP kernel, so currently unused.
@@ -462,20 +461,20 @@ __device__ __forceinline__ void lane_emit(const LaneCfg &L, unsigned tab, double
   exp_ext_scaled<BANK>(fma(-(d * d), L.mc, L.ac), tab, p, kk);
 }
 
-template <int MEL, int MODE, bool WITH_JOIN, int PH, bool FWD_ONLY>
+template <int MEL, int MODE, bool WITH_JOIN, bool FWD_ONLY>
 __device__ __forceinline__ void lane_update(const LaneCfg &L, LaneState<MEL> &S, int c, double p, int kk,
                                             const LaneOut &in, double sF, int sX, LaneOut &out, XD &aout);
 
-template <int MEL, int MODE, bool WITH_JOIN, int PH, bool FWD_ONLY>
+template <int MEL, int MODE, bool WITH_JOIN, bool FWD_ONLY>
 __device__ __forceinline__ void lane_step(const LaneCfg &L, LaneState<MEL> &S, unsigned tab, int c, double x,
                                           const LaneOut &in, double sF, int sX, LaneOut &out, XD &aout) {
   double p;
   int kk;
   lane_emit<true>(L, tab, x, p, kk);  // lane_step is the SNP kernel's form
-  lane_update<MEL, MODE, WITH_JOIN, PH, FWD_ONLY>(L, S, c, p, kk, in, sF, sX, out, aout);
+  lane_update<MEL, MODE, WITH_JOIN, FWD_ONLY>(L, S, c, p, kk, in, sF, sX, out, aout);
 }
 
-template <int MEL, int MODE, bool WITH_JOIN, int PH, bool FWD_ONLY>
+template <int MEL, int MODE, bool WITH_JOIN, bool FWD_ONLY>
 __device__ __forceinline__ void lane_update(const LaneCfg &L, LaneState<MEL> &S, int c, double p, int kk,
                                             const LaneOut &in, double sF, int sX, LaneOut &out, XD &aout) {
   out.p = p;
@@ -516,7 +515,6 @@ __device__ __forceinline__ void lane_update(const LaneCfg &L, LaneState<MEL> &S,
   // instead of m + 1, and every in-flight value is computed straight into its next slot (no shifting moves: the
   // delay line of the unfactored form cost 6 register moves per step at m = 2).  S.q[0] = A of the previous step,
   // S.q[i] = Q_i.
-  static_assert(PH < 0, "the delay line needs no phase any more");
   if (MEL == 0) {
     S.mod = xd_add(xd_make(pb * S.mod.f, S.mod.e + kb), push);
   } else {
@@ -531,7 +529,8 @@ __device__ __forceinline__ void lane_update(const LaneCfg &L, LaneState<MEL> &S,
   out.E = inb ? S.mod.e : NVB_EZERO;
 }
 
-// Mantissa renormalisation (call on a warp-uniform schedule, every 32 steps).
+// Mantissa renormalisation (call on a warp-uniform schedule: every NVB_RENORM_MASK + 1 steps in the sweeps, every 16 in
+// the SNP kernel).
 template <int MEL>
 __device__ __forceinline__ void lane_renorm(LaneState<MEL> &S) {
   xd_renorm(S.mod);

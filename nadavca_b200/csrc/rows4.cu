@@ -226,7 +226,7 @@ __device__ __forceinline__ void sweep_stripes(const ModelDev &M, const ReadView 
       lane_emit(L, exp_tab, ring_read(R, sample_index(t + 1)), p_cur, k_cur);
       LaneOut in = shfl_up_out<MODE>(out);
       XD aout;
-      lane_update<MEL, MODE, false, -1, false>(L, S, c, p, kk, in, 1.0, 0, out, aout);
+      lane_update<MEL, MODE, false, false>(L, S, c, p, kk, in, 1.0, 0, out, aout);
       if (lane == 0) {
         const bool inb = (c >= L.ms && c <= L.me);
         out.f = inb ? 1.0 : 0.0;

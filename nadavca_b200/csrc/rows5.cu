@@ -221,7 +221,7 @@ __device__ __forceinline__ void slot_step(Slot<MEL> &Q, const ReadView &v, const
   in.E = ones ? 0 : (m0 ? in0.E : (m1 ? in1.E : NVB_EZERO));
   in.p = m0 ? in0.p : (m1 ? in1.p : 1.0);
   in.k = m0 ? in0.k : (m1 ? in1.k : 0);
-  lane_update<MEL, MODE, false, -1, false>(Q.L, Q.S, c, p, kk, in, 1.0, 0, Q.out, Q.aout);
+  lane_update<MEL, MODE, false, false>(Q.L, Q.S, c, p, kk, in, 1.0, 0, Q.out, Q.aout);
 }
 
 template <int MODE>

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(128) snp3_kernel(ModelDev M, BatchDev B, int b
       }
       XD aout;
       // JOIN lanes multiply their A-row cell by the closing suffix cell, every other lane by (1.0, 0)
-      lane_step<MEL, MODE, true, -1, false>(L, S, exp_tab, c, x, in, is_join ? rF : 1.0, is_join ? rX : 0, res, aout);
+      lane_step<MEL, MODE, true, false>(L, S, exp_tab, c, x, in, is_join ? rF : 1.0, is_join ? rX : 0, res, aout);
       if (is_loader) {  // the loader's output is the stored prefix row (zero outside its band)
         res.f = rF; res.E = rX;
       } else if (!passes) {
