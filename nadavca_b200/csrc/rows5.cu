@@ -38,11 +38,12 @@ namespace {
 #endif
 __host__ __device__ constexpr int tile_steps(int mode) { return mode == NVB_MODE_PLAIN ? NVB_ROT_TS_PLAIN : NVB_ROT_TS_OTHER; }
 
+// What the transposing flush needs to know about the row a lane parked in a store tile, reduced to the step index: the
+// cell of step tt lies at plane index base + tt (forward) / base - tt (reverse) and is inside the row's band for
+// t_lo <= tt <= t_hi (an empty range for lanes that store nothing).  16 bytes: one shared-memory load per flushed cell.
 struct RowMeta {
-  long long off;  // offset of the row's first cell in the matrix planes
-  int s, e;       // band of the row (empty for lanes that store nothing)
-  int pair;       // pair index of the lane's slot: column at step t is C0 +- (t - pair)
-  int pad;
+  long long base;
+  int t_lo, t_hi;
 };
 struct StoreTile {
   double *f;      // [32][TS + 1]
@@ -64,6 +65,8 @@ struct PairRec {
   double mu, ac, mc, flags;  // BatchDev::row_emis[i]
 };
 static_assert(sizeof(PairRec) == 64, "PairRec layout");
+static_assert((2 * tile_bytes(NVB_ROT_TS_PLAIN)) % 256 == 0 && (2 * tile_bytes(NVB_ROT_TS_OTHER)) % 256 == 0,
+              "the signal ring behind the store tiles must start on a 256-byte boundary (TMA bulk copies)");
 // per warp: store tiles | signal ring | 32 PairRec
 __host__ __device__ constexpr size_t rec_offset(int mode) {
   return ((tiles_per_warp(mode) * tile_bytes(tile_steps(mode)) + ring_bytes(8) + 15) / 16) * 16;
@@ -100,9 +103,8 @@ __device__ __forceinline__ void flush_tile(const StoreTile &tile, double *F, int
     const int r = RPI * i + lane / TS;
     const RowMeta m = tile.meta[r];
     const int tt = t0 + kk;
-    const int c = REV ? C0 - (tt - m.pair) : C0 + (tt - m.pair);
-    if (c >= m.s && c <= m.e) {
-      const long long idx = m.off + (c - m.s);
+    if (tt >= m.t_lo && tt <= m.t_hi) {
+      const long long idx = REV ? m.base - tt : m.base + tt;
       F[idx] = tile.f[r * TSTRIDE + kk];
       X[idx] = tile.x[r * TSTRIDE + kk];
     }
@@ -238,17 +240,23 @@ __device__ __forceinline__ LaneOut rotate_out(const LaneOut &o, int src) {
   return r;
 }
 
-template <int MEL>
-__device__ __forceinline__ void write_meta(const StoreTile &tb, const StoreTile &ta, const Slot<MEL> &Q, int lane,
-                                           bool trans) {
+// Row [s, e] at plane offset `off`, swept by pair `pair`: column at step tt is C0 + (tt - pair) forward, C0 - (tt - pair)
+// in reverse, plane index off + (column - s).
+template <bool REV>
+__device__ __forceinline__ RowMeta row_meta(bool live, long long off, int s, int e, int pair, int C0) {
   RowMeta m;
+  if (REV) { m.base = off - s + C0 + pair; m.t_lo = C0 + pair - e; m.t_hi = C0 + pair - s; }
+  else { m.base = off - s + C0 - pair; m.t_lo = s - C0 + pair; m.t_hi = e - C0 + pair; }
+  if (!live) { m.t_lo = 1; m.t_hi = 0; }
+  return m;
+}
+
+template <int MEL, bool REV>
+__device__ __forceinline__ void write_meta(const StoreTile &tb, const StoreTile &ta, const Slot<MEL> &Q, int lane,
+                                           bool trans, int C0) {
   const bool live = Q.pair >= 0;
-  m.off = Q.boff; m.s = live ? Q.L.ms : 1; m.e = live ? Q.L.me : 0; m.pair = live ? Q.pair : 0; m.pad = 0;
-  tb.meta[lane] = m;
-  if (trans) {
-    m.off = Q.aoff; m.s = live ? Q.ws : 1; m.e = live ? Q.awe : 0;
-    ta.meta[lane] = m;
-  }
+  tb.meta[lane] = row_meta<REV>(live, Q.boff, Q.L.ms, Q.L.me, Q.pair, C0);
+  if (trans) ta.meta[lane] = row_meta<REV>(live, Q.aoff, Q.ws, Q.awe, Q.pair, C0);
 }
 
 template <int MEL, int MODE, bool REV>
@@ -319,8 +327,8 @@ __device__ void sweep_rotate(const ModelDev &M, const ReadView &v, double *F, in
         if (next_g < n) rec_prefetch(rec, v, pair_base<REV>(n, next_g));  // its record was read into the slot above
       }
       any2_tile = __any_sync(NVB_FULL, Q2.pair >= 0);
-      write_meta(tPB, tPA, P, lane, TRANS);
-      if (any2_tile) write_meta(tSB, tSA, Q2, lane, TRANS);
+      write_meta<MEL, REV>(tPB, tPA, P, lane, TRANS, C0);
+      if (any2_tile) write_meta<MEL, REV>(tSB, tSA, Q2, lane, TRANS, C0);
       __syncwarp();
     }
     if (!any2_tile) {
@@ -411,7 +419,7 @@ __global__ void __launch_bounds__(64, NVB_ROT_MIN_BLOCKS) sweep5_kernel(ModelDev
 template <int MEL, int MODE>
 void launch_mode(const ModelDev &M, const BatchDev &B, int b0, int n_items, const int64_t *mb, double *pF, int32_t *pX,
                  double *sF, int32_t *sX, cudaStream_t st) {
-  const int warps = 2;  // 2 x (2 tiles x 4.2 KB + 2 KB ring + 2 KB pair records) = 25 KB per CTA (42 KB in the transition
+  const int warps = 2;  // 2 x (2 tiles x 3.9 KB + 2 KB ring + 2 KB pair records) = 24 KB per CTA (40 KB in the transition
                         // sweep): 8 CTAs per SM (5) beside the 2 KB exp table and the 1 KB the driver reserves per CTA
   const size_t smem = (size_t)warps * warp_bytes(MODE);
   sweep5_kernel<MEL, MODE><<<(n_items + warps - 1) / warps, warps * NVB_WARP, smem, st>>>(M, B, b0, n_items, mb, pF, pX,
